@@ -1,0 +1,80 @@
+"""Generate the field headers and compile libmodarith_b200.so for sm_100a, in-tree.
+
+The reference's build step is "run the generator, compile what it printed"
+(pseudo.py:1694-1702, 1895-1903); ours is the same with nvcc:
+
+    python -m modarith_b200.build            # regenerate + compile if stale
+    python -m modarith_b200.build --force
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libmodarith_b200.so")
+OBJDIR = os.path.join(PKG, "build")
+
+NVCC_FLAGS = ["-I", CSRC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+UNITS = ["mab_capi_X25519.cu", "mab_capi_X448.cu", "mab_capi_NIST256.cu", "mab_runtime.cu"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def _digest():
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    roots = [CSRC, os.path.join(CSRC, "gen"), os.path.join(PKG, "..", "include")]
+    for root in roots:
+        for fn in sorted(os.listdir(root)):
+            p = os.path.join(root, fn)
+            if os.path.isfile(p) and fn.endswith((".cu", ".cuh", ".inc", ".h")):
+                h.update(fn.encode())
+                h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=True):
+    from .gen.cli import generate_all
+    generate_all(verbose=False)
+    stamp = os.path.join(OBJDIR, "digest.txt")
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return LIB
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(unit):
+        obj = os.path.join(OBJDIR, unit.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", os.path.join(CSRC, unit), "-o", obj]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        with open(obj + ".log", "w") as f:
+            f.write(r.stdout)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (unit, r.stdout[-4000:]))
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(cmd)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    if verbose:
+        print("built", LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,6 @@
+// C ABI instantiation for NIST256: generated field code + hand-written kernels.
+#include "gen/field_NIST256.cuh"
+#define MAB_P NIST256
+#define MAB_F F_NIST256
+
+#include "mab_capi.inc"

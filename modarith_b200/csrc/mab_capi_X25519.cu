@@ -1,0 +1,6 @@
+// C ABI instantiation for X25519: generated field code + hand-written kernels.
+#include "gen/field_X25519.cuh"
+#define MAB_P X25519
+#define MAB_F F_X25519
+#define MAB_HAS_CURVE 1
+#include "mab_capi.inc"

@@ -1,0 +1,6 @@
+// C ABI instantiation for X448: generated field code + hand-written kernels.
+#include "gen/field_X448.cuh"
+#define MAB_P X448
+#define MAB_F F_X448
+#define MAB_HAS_CURVE 1
+#include "mab_capi.inc"

@@ -1,0 +1,184 @@
+// mab_kernels.cuh -- batched kernels: one field element / one key per thread.
+//
+// HBM layout.  Field elements are structure-of-arrays LIMB PLANES: limb j of element i is
+// plane[j*stride + i] (uint32), so a warp's load of limb j is one coalesced 128-byte
+// line; every kernel issues its F::L (x operands) independent plane loads up front.
+// Byte strings keep the reference's array-of-structures layout (element i at
+// bytes[i*Nbytes ..], modimp/modexp big-endian, rfc7748 little-endian) and are moved with
+// the widest vector access the pointer alignment allows.
+#pragma once
+#include <cuda_runtime.h>
+#include "rfc7748_sm100.cuh"
+
+enum MabOp {
+  OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_SQR, OP_MLI, OP_CPY, OP_NSQR, OP_PRO, OP_INV, OP_INVH,
+  OP_QR, OP_QRH, OP_SQRT, OP_SQRTH, OP_IS1, OP_IS0, OP_ZER, OP_ONE, OP_INT, OP_NRES, OP_REDC,
+  OP_CSW, OP_CMV, OP_SHL, OP_SHR, OP_HAF, OP_2R, OP_SIGN, OP_CMP, OP_FSB
+};
+
+struct MabArgs {
+  const uint32_t* a;     // first input planes
+  const uint32_t* b;     // second input planes (or h)
+  uint32_t* r;           // output planes (may alias a or b)
+  uint32_t* r2;          // second in/out planes (modcsw)
+  int* iout;             // per-element int results
+  const int* iin;        // per-element int inputs (swap / move bits)
+  uint32_t scalar;       // small-integer argument
+  size_t n, stride;
+};
+
+template <int L> static __device__ __forceinline__ void plane_ld(uint32_t (&x)[L], const uint32_t* p, size_t stride, size_t i) {
+#pragma unroll
+  for (int j = 0; j < L; j++) x[j] = p[j * stride + i];
+}
+template <int L> static __device__ __forceinline__ void plane_st(uint32_t* p, size_t stride, size_t i, const uint32_t (&x)[L]) {
+#pragma unroll
+  for (int j = 0; j < L; j++) p[j * stride + i] = x[j];
+}
+
+template <class F, int OP> __global__ void __launch_bounds__(128) k_field(MabArgs p) {
+  constexpr int L = F::L;
+  typedef Field<F> Fd;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  uint32_t a[L], b[L], r[L];
+  if constexpr (OP == OP_ADD || OP == OP_SUB || OP == OP_MUL || OP == OP_CMP || OP == OP_INVH ||
+                OP == OP_SQRTH || OP == OP_QRH) {
+    plane_ld<L>(a, p.a, p.stride, i);
+    plane_ld<L>(b, p.b, p.stride, i);
+  } else if constexpr (OP == OP_ZER || OP == OP_ONE || OP == OP_INT || OP == OP_2R) {
+  } else if constexpr (OP == OP_CSW || OP == OP_CMV) {
+    plane_ld<L>(a, p.a, p.stride, i);
+    plane_ld<L>(b, p.r2, p.stride, i);
+  } else {
+    plane_ld<L>(a, p.a, p.stride, i);
+  }
+  if constexpr (OP == OP_ADD) F::add(r, a, b);
+  if constexpr (OP == OP_SUB) F::sub(r, a, b);
+  if constexpr (OP == OP_NEG) F::neg(r, a);
+  if constexpr (OP == OP_MUL) F::mul(r, a, b);
+  if constexpr (OP == OP_SQR) F::sqr(r, a);
+  if constexpr (OP == OP_MLI) F::mli(r, a, p.scalar);
+  if constexpr (OP == OP_CPY) Fd::cpy(r, a);
+  if constexpr (OP == OP_NSQR) { Fd::cpy(r, a); Fd::nsqr(r, (int)p.scalar); }
+  if constexpr (OP == OP_PRO) F::pro(r, a);
+  if constexpr (OP == OP_INV) Fd::template inv<false>(r, a, a);
+  if constexpr (OP == OP_INVH) Fd::template inv<true>(r, a, b);
+  if constexpr (OP == OP_SQRT) Fd::template sqrt<false>(r, a, a);
+  if constexpr (OP == OP_SQRTH) Fd::template sqrt<true>(r, a, b);
+  if constexpr (OP == OP_ZER) Fd::zer(r);
+  if constexpr (OP == OP_ONE) Fd::one(r);
+  if constexpr (OP == OP_INT) Fd::from_int(r, p.scalar);
+  if constexpr (OP == OP_2R) Fd::pow2(r, p.scalar);
+  if constexpr (OP == OP_NRES) F::nres(r, a);
+  if constexpr (OP == OP_REDC) Fd::to_words(r, a);
+  if constexpr (OP == OP_HAF) { Fd::cpy(r, a); Fd::haf(r); }
+  if constexpr (OP == OP_SHL) { Fd::cpy(r, a); Fd::shl(r, p.scalar); }
+  if constexpr (OP == OP_SHR) { Fd::cpy(r, a); uint32_t o = Fd::shr(r, p.scalar); if (p.iout) p.iout[i] = (int)o; }
+  if constexpr (OP == OP_FSB) { Fd::cpy(r, a); uint32_t o = Fd::fsb(r); if (p.iout) p.iout[i] = (int)o; }
+  if constexpr (OP == OP_QR) { p.iout[i] = (int)Fd::template qr<false>(a, a); return; }
+  if constexpr (OP == OP_QRH) { p.iout[i] = (int)Fd::template qr<true>(a, b); return; }   // a = h, b = x
+  if constexpr (OP == OP_IS1) { p.iout[i] = (int)Fd::is1(a); return; }
+  if constexpr (OP == OP_IS0) { p.iout[i] = (int)Fd::is0(a); return; }
+  if constexpr (OP == OP_SIGN) { p.iout[i] = (int)Fd::sign(a); return; }
+  if constexpr (OP == OP_CMP) { p.iout[i] = (int)Fd::cmp(a, b); return; }
+  if constexpr (OP == OP_CSW) {
+    Fd::csw((uint32_t)p.iin[i] & 1u, a, b);
+    plane_st<L>(p.r, p.stride, i, a);
+    plane_st<L>(p.r2, p.stride, i, b);
+    return;
+  }
+  if constexpr (OP == OP_CMV) {          // f(r2) <- g(a) iff bit
+    Fd::cmv((uint32_t)p.iin[i] & 1u, a, b);
+    plane_st<L>(p.r2, p.stride, i, b);
+    return;
+  }
+  plane_st<L>(p.r, p.stride, i, r);
+}
+
+// ---- byte strings ------------------------------------------------------------------
+// NW words of element i from an AoS byte array (element size 4*NW bytes), widest aligned access.
+template <int NW> static __device__ __forceinline__ void aos_ld(uint32_t (&w)[NW], const uint8_t* base, size_t i, unsigned align) {
+  const uint8_t* e = base + i * (size_t)(4 * NW);
+  if (NW % 4 == 0 && align >= 16) {
+#pragma unroll
+    for (int j = 0; j < NW / 4; j++) {
+      uint4 v = reinterpret_cast<const uint4*>(e)[j];
+      w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+  } else if (NW % 2 == 0 && align >= 8) {
+#pragma unroll
+    for (int j = 0; j < NW / 2; j++) {
+      uint2 v = reinterpret_cast<const uint2*>(e)[j];
+      w[2 * j] = v.x; w[2 * j + 1] = v.y;
+    }
+  } else if (align >= 4) {
+#pragma unroll
+    for (int j = 0; j < NW; j++) w[j] = reinterpret_cast<const uint32_t*>(e)[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < NW; j++)
+      w[j] = (uint32_t)e[4 * j] | ((uint32_t)e[4 * j + 1] << 8) | ((uint32_t)e[4 * j + 2] << 16) | ((uint32_t)e[4 * j + 3] << 24);
+  }
+}
+template <int NW> static __device__ __forceinline__ void aos_st(uint8_t* base, size_t i, unsigned align, const uint32_t (&w)[NW]) {
+  uint8_t* e = base + i * (size_t)(4 * NW);
+  if (NW % 4 == 0 && align >= 16) {
+#pragma unroll
+    for (int j = 0; j < NW / 4; j++) reinterpret_cast<uint4*>(e)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  } else if (NW % 2 == 0 && align >= 8) {
+#pragma unroll
+    for (int j = 0; j < NW / 2; j++) reinterpret_cast<uint2*>(e)[j] = make_uint2(w[2 * j], w[2 * j + 1]);
+  } else if (align >= 4) {
+#pragma unroll
+    for (int j = 0; j < NW; j++) reinterpret_cast<uint32_t*>(e)[j] = w[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+      e[4 * j] = (uint8_t)w[j]; e[4 * j + 1] = (uint8_t)(w[j] >> 8); e[4 * j + 2] = (uint8_t)(w[j] >> 16); e[4 * j + 3] = (uint8_t)(w[j] >> 24);
+    }
+  }
+}
+
+// modimp (pseudo.py:1130-1146): big-endian Nbytes -> planes; status[i] = 1 iff value < p
+template <class F> __global__ void __launch_bounds__(128) k_imp(const uint8_t* bytes, uint32_t* r, int* status, size_t n, size_t stride, unsigned align) {
+  constexpr int L = F::L;
+  static_assert(F::NBYTES == 4 * L, "byte strings are whole words for the supported moduli");
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t raw[L], w[L], a[L];
+  aos_ld<L>(raw, bytes, i, align);
+#pragma unroll
+  for (int j = 0; j < L; j++) w[j] = mab_bswap(raw[L - 1 - j]);
+  uint32_t lt = Field<F>::from_words(a, w);
+  plane_st<L>(r, stride, i, a);
+  if (status) status[i] = (int)lt;
+}
+// modexp (pseudo.py:1115-1127): planes -> canonical big-endian Nbytes
+template <class F> __global__ void __launch_bounds__(128) k_exp(const uint32_t* ap, uint8_t* bytes, size_t n, size_t stride, unsigned align) {
+  constexpr int L = F::L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[L], w[L], raw[L];
+  plane_ld<L>(a, ap, stride, i);
+  Field<F>::to_words(w, a);
+#pragma unroll
+  for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(w[j]);
+  aos_st<L>(bytes, i, align, raw);
+}
+
+// rfc7748 (rfc7748.c:156): bv[i] = clamp(bk[i]) * bu[i], little-endian Nbytes strings
+#ifndef MAB_LADDER_THREADS
+#define MAB_LADDER_THREADS 128
+#endif
+template <class F> __global__ void __launch_bounds__(MAB_LADDER_THREADS) k_rfc7748(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
+  constexpr int L = F::L;
+  static_assert(F::NBYTES == 4 * L, "byte strings are whole words for the supported curves");
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[L], u[L], out[L];
+  aos_ld<L>(k, bk, i, align);
+  aos_ld<L>(u, bu, i, align);
+  Rfc7748<F>::scalarmult(out, k, u);
+  aos_st<L>(bv, i, align, out);
+}

@@ -1,0 +1,89 @@
+// rfc7748_sm100.cuh -- RFC 7748 Montgomery ladder, one key per thread, state in registers.
+//
+// Counterpart of rfc7748.c:156-256 (and of the <<<2,1>>> demo kernel
+// simd/rfc7748_simt.cu:155-226, whose 13 field elements live in a 432-byte local-memory
+// frame behind 522 calls).  Here the step keeps 4 persistent elements (x2,z2,x3,z3) plus
+// x1 and 4 temporaries, all in registers, every field call inlined into straight-line
+// IMAD.WIDE chains; the scalar is consumed by shifting it left one bit per step so no
+// register is indexed dynamically; cswap is the mask form (pseudo.py:1006-1013).
+#pragma once
+#include "mab_field.cuh"
+
+template <class F> struct Rfc7748 {
+  static constexpr int L = F::L;
+  typedef Field<F> Fd;
+
+  // clamp (rfc7748.c:135-141) on little-endian words
+  static MAB_DEV void clamp(uint32_t (&k)[L]) {
+    constexpr int s = (8 - (F::NBITS % 8)) % 8;
+    k[0] &= ~((1u << F::COF) - 1u);
+    constexpr uint32_t topmask = ((0xffu >> s) << 24) | 0x00ffffffu;
+    k[L - 1] &= topmask;
+    k[L - 1] |= (0x80u >> s) << 24;
+  }
+
+  // One scalar multiplication.  k, u: little-endian byte strings as words; out likewise.
+  static MAB_DEV void scalarmult(uint32_t (&out)[L], uint32_t (&k)[L], uint32_t (&u)[L]) {
+    // mask() (rfc7748.c:148-152,172): drop the bits above Nbits in the top byte of u
+    constexpr int rbits = (F::NBITS % 8) ? (F::NBITS % 8) : 8;
+    u[L - 1] &= ((((1u << rbits) - 1u) << 24) | 0x00ffffffu);
+    clamp(k);
+
+    uint32_t x1[L], x2[L], z2[L], x3[L], z3[L];
+    (void)Fd::from_words(x1, u);                 // modimp (rfc7748.c:178)
+    Fd::one(x2);
+    Fd::zer(z2);
+    Fd::cpy(x3, x1);
+    Fd::one(z3);
+
+    // align bit Nbits-1 of the scalar with bit 31 of the top word
+    constexpr int lead = 32 * L - F::NBITS;
+    if (lead > 0) {
+#pragma unroll
+      for (int j = L - 1; j > 0; j--) k[j] = mab_shf_l(k[j - 1], k[j], lead);
+      k[0] <<= lead;
+    }
+
+    uint32_t swap = 0;
+    MAB_NOUNROLL
+    for (int i = F::NBITS - 1; i >= 0; i--) {    // rfc7748.c:186-221
+      uint32_t kt = k[L - 1] >> 31;
+#pragma unroll
+      for (int j = L - 1; j > 0; j--) k[j] = mab_shf_l(k[j - 1], k[j], 1);
+      k[0] <<= 1;
+      swap ^= kt;
+      Fd::csw(swap, x2, x3);
+      Fd::csw(swap, z2, z3);
+      swap = kt;
+
+      uint32_t A[L], B[L], C[L], D[L];
+      F::add(A, x2, z2);                         // A = x2+z2
+      F::sub(B, x2, z2);                         // B = x2-z2
+      F::add(C, x3, z3);                         // C = x3+z3
+      F::sub(D, x3, z3);                         // D = x3-z3
+      F::mul(D, D, A);                           // DA
+      F::mul(C, C, B);                           // CB
+      F::sqr(A, A);                              // AA
+      F::sqr(B, B);                              // BB
+      F::add(x3, D, C);
+      F::sub(z3, D, C);
+      F::sqr(x3, x3);                            // x3 = (DA+CB)^2
+      F::sqr(z3, z3);
+      F::mul(z3, z3, x1);                        // z3 = x1*(DA-CB)^2
+      F::mul(x2, A, B);                          // x2 = AA*BB
+      F::sub(B, A, B);                           // E = AA-BB
+      F::mli(z2, B, F::A24);                     // a24*E
+      F::add(z2, z2, A);
+      F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
+    }
+    Fd::csw(swap, x2, x3);
+    Fd::csw(swap, z2, z3);
+
+    // TWIST_SECURE branch (rfc7748.c:225-227,252): x2/z2 with 0 -> 0
+    uint32_t h[L];
+    F::pro(h, z2);
+    Fd::template inv<true>(z2, z2, h);
+    F::mul(x2, x2, z2);
+    Fd::to_words(out, x2);                       // modexp (rfc7748.c:254)
+  }
+};

@@ -1,0 +1,136 @@
+"""Print one modulus' field code as a CUDA header (`field_<NAME>.cuh`).
+
+Counterpart of `functions()` in the reference generators (pseudo.py:1413-1445,
+monty.py:1885-1918), which print ~32 C functions for one prime.  Here the
+prime-specific arithmetic (mul/sqr/mli/add/sub/neg/canon as inline-PTX blocks, the
+modpro addition chain, the constants) is printed as a struct `F_<NAME>` of static
+device functions, and the prime-independent functions of the API (modinv, modsqrt,
+modqr, modimp/modexp, cswap, the RFC 7748 ladder, ...) are hand-written templates
+over that struct in csrc/mab_field.cuh and csrc/rfc7748_sm100.cuh -- the same split
+as the reference's generated field.c + hand-written rfc7748.c.
+"""
+from __future__ import annotations
+
+from .. import addchain
+from .plan import Plan, words
+
+
+def _arr(name, L, const=False):
+    return "%suint32_t (&%s)[%d]" % ("const " if const else "", name, L)
+
+
+def _block_fn(plan: Plan, fname, asm, sig, ret=None):
+    s = "  static MAB_DEV %s %s(%s) {\n" % ("uint32_t" if ret else "void", fname, sig)
+    if ret:
+        s += "    uint32_t %s;\n" % ret
+    s += "#ifndef MAB_HOSTSIM\n"
+    s += asm.emit_cuda("    ")
+    s += "#else\n"
+    s += asm.emit_sim("    ")
+    s += "#endif\n"
+    if ret:
+        s += "    return %s;\n" % ret
+    s += "  }\n\n"
+    return s
+
+
+def _const_fn(fname, ws, L):
+    body = " ".join("r[%d] = 0x%08xu;" % (i, w) for i, w in enumerate(ws))
+    return "  static MAB_DEV void %s(%s) { %s }\n" % (fname, _arr("r", L), body)
+
+
+def emit_field_header(plan: Plan) -> str:
+    P, L = plan.P, plan.L
+    blocks = plan.build()
+    plan.self_check(trials=120)
+    prog = addchain.find_chain(P.pe)
+    assert addchain.evaluate(prog, 3, P.p) == pow(3, P.pe, P.p)
+    nsq, nmu = addchain.cost(prog)
+    S = "F_" + P.name
+    out = []
+    out.append("// Automatically generated field arithmetic for sm_100a -- do not edit.\n")
+    out.append("// Command line : python -m modarith_b200.gen.%s_sm100 %s\n" %
+               ("pseudo" if P.family == "pseudo" else "monty", P.name))
+    out.append("// modulus %s = 0x%x\n" % (P.name, P.p))
+    out.append("// plan %s: %d saturated 32-bit limbs; stored values < %s; R = 2^%d\n" % (
+        type(plan).__name__, L, "p" if plan.bound == P.p else "2^%d" % (32 * L),
+        plan.R.bit_length() - 1))
+    for k in ("mul", "sqr", "mli", "add", "sub", "canon"):
+        w, i, a = blocks[k].stats()
+        out.append("//   %-5s : %3d IMAD.WIDE  %2d IMAD  ~%3d ALU-pipe ops\n" % (k, w, i, a))
+    out.append("//   modpro: %d squarings + %d multiplies (exponent (p-1-2^k)/2^(k+1), k=%d)\n" %
+               (nsq, nmu, P.pm1d2))
+    out.append("#pragma once\n#include \"mab_common.cuh\"\n\n")
+    out.append("struct %s {\n" % S)
+    out.append("  static constexpr int L = %d;\n" % L)
+    out.append("  static constexpr int NBITS = %d;\n" % P.nbits)
+    out.append("  static constexpr int NBYTES = %d;\n" % P.nbytes)
+    out.append("  static constexpr int PM1D2 = %d;\n" % P.pm1d2)
+    out.append("  static constexpr bool MONTGOMERY = %s;\n" % ("true" if plan.R != 1 else "false"))
+    out.append("  static constexpr int PRO_SQR = %d, PRO_MUL = %d;\n" % (nsq, nmu))
+    if P.a24 is not None:
+        out.append("  static constexpr bool HAS_CURVE = true;\n")
+        out.append("  static constexpr uint32_t A24 = %d;\n" % P.a24)
+        out.append("  static constexpr int COF = %d;\n" % P.cof)
+        out.append("  static constexpr uint32_t GENERATOR = %d;\n" % P.generator)
+    else:
+        out.append("  static constexpr bool HAS_CURVE = false;\n")
+        out.append("  static constexpr uint32_t A24 = 0;\n  static constexpr int COF = 0;\n"
+                   "  static constexpr uint32_t GENERATOR = 0;\n")
+    out.append("  static const char* name() { return \"%s\"; }\n\n" % P.name)
+
+    a, b, r = _arr("a", L, True), _arr("b", L, True), _arr("r", L)
+    out.append("  // c = a*b (pseudo.py:616-659 / monty.py:663-872)\n")
+    out.append(_block_fn(plan, "mul", blocks["mul"], "%s, %s, %s" % (r, a, b)))
+    out.append("  // c = a*a (pseudo.py:663-702 / monty.py:982-1165)\n")
+    out.append(_block_fn(plan, "sqr", blocks["sqr"], "%s, %s" % (r, a)))
+    out.append("  // c = a*b for a small integer b (pseudo.py:705-728 / monty.py:876-978)\n")
+    out.append(_block_fn(plan, "mli", blocks["mli"], "%s, %s, uint32_t b" % (r, a)))
+    out.append("  // n = a+b (pseudo.py:286-304)\n")
+    out.append(_block_fn(plan, "add", blocks["add"], "%s, %s, %s" % (r, a, b)))
+    out.append("  // n = a-b (pseudo.py:307-326)\n")
+    out.append(_block_fn(plan, "sub", blocks["sub"], "%s, %s, %s" % (r, a, b)))
+    out.append("  // n = -b (pseudo.py:329-348)\n")
+    out.append(_block_fn(plan, "neg", blocks["neg"], "%s, %s" % (r, b)))
+    out.append("  // canonical residue of a stored value; returns 1 iff it was already < p\n"
+               "  // (flatten/modfsb, pseudo.py:255-283)\n")
+    out.append(_block_fn(plan, "canon", blocks["canon"], "%s, %s" % (r, a), ret="lt"))
+
+    out.append(_const_fn("set_p", words(P.p, L), L))
+    out.append(_const_fn("set_one", words(plan.to_internal(1), L), L))
+    out.append(_const_fn("set_roi", words(plan.to_internal(P.roi), L), L))
+    out.append(_const_fn("set_r2", words(plan.R * plan.R % P.p, L), L))
+    out.append("\n")
+    if plan.R != 1:
+        out.append("  // nres: multiply by R^2 mod p (monty.py:1386-1399); redc: multiply by 1 (monty.py:1402-1416)\n")
+        out.append("  static MAB_DEV void nres(%s, %s) { uint32_t c[L]; set_r2(c); mul(r, a, c); }\n" % (r, a))
+        out.append("  static MAB_DEV void redc(%s, %s) { uint32_t c[L]; c[0] = 1;\n"
+                   "    for (int i = 1; i < L; i++) c[i] = 0;\n    mul(r, a, c); }\n\n" % (r, a))
+    else:
+        out.append("  // nres: copy (pseudo.py:952-962); redc: copy + final subtract (pseudo.py:965-976)\n")
+        out.append("  static MAB_DEV void nres(%s, %s) { for (int i = 0; i < L; i++) r[i] = a[i]; }\n" % (r, a))
+        out.append("  static MAB_DEV void redc(%s, %s) { (void)canon(r, a); }\n\n" % (r, a))
+
+    # progenitor chain (pseudo.py:758-785)
+    tmps = addchain.temporaries(prog)
+    out.append("  // z = w^PE, straight-line addition chain (pseudo.py:758-785; our own chain finder)\n")
+    out.append("  static MAB_DEV void pro(%s, %s) {\n" % (_arr("z", L), _arr("w", L, True)))
+    out.append("    uint32_t x[L];\n    for (int i = 0; i < L; i++) x[i] = w[i];\n")
+    for t in tmps:
+        out.append("    uint32_t %s[L];\n" % t)
+    for op in prog:
+        if op[0] == "mul":
+            out.append("    mul(%s, %s, %s);\n" % (op[1], op[2], op[3]))
+        else:
+            dst, src, n = op[1], op[2], op[3]
+            if n == 0:
+                out.append("    for (int i = 0; i < L; i++) %s[i] = %s[i];\n" % (dst, src))
+            else:
+                out.append("    sqr(%s, %s);\n" % (dst, src))
+                if n == 2:
+                    out.append("    sqr(%s, %s);\n" % (dst, dst))
+                elif n > 2:
+                    out.append("    MAB_NOUNROLL\n    for (int i = 1; i < %d; i++) sqr(%s, %s);\n" % (n, dst, dst))
+    out.append("  }\n")
+    out.append("};\n")
+    return "".join(out)

@@ -1,0 +1,588 @@
+"""Limb plans: how one modulus maps onto 32-bit registers of an sm_100a thread.
+
+The reference picks an UNSATURATED radix (getbase, pseudo.py:124-140: 29-bit limbs
+x 9 for 255/256-bit moduli, 28 x 16 for 448 bits at WL=32) because portable C has
+no carry flag.  sm_100a has one (`IMAD.WIDE.U32.X`, `IADD3.X` carry predicates),
+and the roofline is counted in L^2 products with L = ceil(Nbits/32) (SURVEY.md
+section 8d), so the plans here use L saturated 32-bit limbs -- 8 for 2^255-19 and
+P-256, 14 for 2^448-2^224-1 -- which is 21 % / 23 % fewer wide multiplies than the
+reference's WL=32 layout (64 vs 81, 196 vs 256 per modmul).  The price is that
+there is no spare room for lazy "< 2p" results: every function returns a value
+that fits the L words, and each family keeps its own invariant:
+
+  PseudoMersenne  2^n - c, 32L - n spare bits (X25519: 1).  Weakly reduced:
+                  any representative < 2^(32L).  2^(32L) == c*2^(32L-n) =: fold.
+  GenMersenne     2^(2h) - 2^h - 1 with h a multiple of 32 (X448, h=224).  Weakly
+                  reduced < 2^(2h); 2^(2h) == 2^h + 1, so reduction is additions of
+                  half-length pieces: no multiplies (cf. monty.py:597-627 turning
+                  shaped limbs into adds; we apply the shape directly instead of
+                  through Montgomery form).
+  Montgomery      p == -1 mod 2^32 (P-256): R = 2^(32L), ndash = 1 ("Montgomery
+                  friendly", monty.py:740-751), values kept fully reduced in [0,p).
+
+Each plan builds ptx.Asm blocks for mul/sqr/mli/add/sub/canon and checks them
+against Python bignum arithmetic at generation time (`self_check`).
+"""
+from __future__ import annotations
+
+import random
+
+from ..primes import Prime
+from .ptx import Asm
+from . import satmul
+
+M32 = 0xFFFFFFFF
+
+
+def words(x, n):
+    return [(x >> (32 * i)) & M32 for i in range(n)]
+
+
+def value(ws):
+    return sum(w << (32 * i) for i, w in enumerate(ws))
+
+
+def _names(prefix, n):
+    return ["%s[%d]" % (prefix, i) for i in range(n)]
+
+
+class Plan:
+    family = "?"
+
+    def __init__(self, prime: Prime):
+        self.P = prime
+        self.p = prime.p
+        self.name = prime.name
+        self.L = (prime.nbits + 31) // 32
+        self.bound = 1 << (32 * self.L)      # exclusive bound on stored values (overridden)
+        self.R = 1                           # Montgomery factor (1 = plain residues)
+
+    # -- representation -----------------------------------------------------
+    def to_internal(self, v):                # field value -> stored integer
+        return v * self.R % self.p
+
+    def from_internal(self, w):              # stored integer -> field value
+        return w * pow(self.R, -1, self.p) % self.p
+
+    # -- blocks every plan provides ------------------------------------------
+    def build(self):
+        self.blocks = {
+            "mul": self.build_mul(),
+            "sqr": self.build_sqr(),
+            "mli": self.build_mli(),
+            "add": self.build_add(),
+            "sub": self.build_sub(neg=False),
+            "neg": self.build_sub(neg=True),
+            "canon": self.build_canon(),
+        }
+        return self.blocks
+
+    def _io(self, asm, ins, out="r"):
+        regs = []
+        for nm in ins:
+            ws = _names(nm, self.L)
+            asm.inp(*ws)
+            regs.append(ws)
+        return regs
+
+    def _outs(self, asm, regs, out="r"):
+        for k, r in enumerate(regs):
+            asm.out("%s[%d]" % (out, k), r)
+
+    def build_mul(self):
+        asm = Asm(self.name + ".mul")
+        a, b = self._io(asm, ["a", "b"])
+        T = satmul.product(asm, a, b)
+        self._outs(asm, self.reduce_wide(asm, T))
+        return asm
+
+    def build_sqr(self):
+        asm = Asm(self.name + ".sqr")
+        (a,) = self._io(asm, ["a"])
+        T = satmul.square(asm, a)
+        self._outs(asm, self.reduce_wide(asm, T))
+        return asm
+
+    def build_mli(self):
+        asm = Asm(self.name + ".mli")
+        (a,) = self._io(asm, ["a"])
+        asm.inp("b")
+        T = satmul.times_small(asm, a, "b")
+        self._outs(asm, self.reduce_small(asm, T))
+        return asm
+
+    # -- generation-time verification ---------------------------------------
+    def sample_values(self, rng, n):
+        """Stored-integer samples: edges of the representation plus random ones."""
+        p, B = self.p, self.bound
+        edge = [0, 1, 2, p - 1, p - 2, B - 1, B - 2, (B - 1) ^ 1, 19, 38, 1 << 32, (1 << 32) - 1]
+        edge += [p, p + 1, 2 * p - 1, 2 * p, 2 * p + 1]
+        edge += [value([M32] * k + [0] * (self.L - k)) for k in range(1, self.L)]
+        edge += [value([0] * k + [M32] * (self.L - k)) for k in range(1, self.L)]
+        edge = [e for e in edge if 0 <= e < B]
+        out = list(edge)
+        while len(out) < n:
+            r = rng.random()
+            if r < 0.6:
+                out.append(rng.randrange(B))
+            elif r < 0.8:
+                out.append(value([rng.choice([0, M32, 1, 0x80000000, rng.getrandbits(32)])
+                                  for _ in range(self.L)]) % B)
+            else:
+                out.append((B - 1 - rng.getrandbits(rng.randrange(1, 40))) % B)
+        return out
+
+    def run(self, block, **ins):
+        env = {}
+        for k, v in ins.items():
+            if isinstance(v, list):
+                for i, w in enumerate(v):
+                    env["%s[%d]" % (k, i)] = w
+            else:
+                env[k] = v & M32
+        out = self.blocks[block].run(env)
+        r = value([out["r[%d]" % i] for i in range(self.L)])
+        extra = {k: v for k, v in out.items() if not k.startswith("r[")}
+        return r, extra
+
+    def self_check(self, trials=400, seed=1):
+        rng = random.Random(seed)
+        p, L, B = self.p, self.L, self.bound
+        Rinv = pow(self.R, -1, p)
+        xs = self.sample_values(rng, trials)
+        ys = self.sample_values(rng, trials)
+        rng.shuffle(ys)
+        for x, y in zip(xs, ys):
+            ax, ay = words(x, L), words(y, L)
+            r, _ = self.run("mul", a=ax, b=ay)
+            assert r < B and r % p == x * y * Rinv % p, ("mul", hex(x), hex(y))
+            r, _ = self.run("sqr", a=ax)
+            assert r < B and r % p == x * x * Rinv % p, ("sqr", hex(x))
+            for bb in (0, 1, 2, 121665, 39081, M32, y & M32):
+                r, _ = self.run("mli", a=ax, b=bb)
+                assert r < B and r % p == x * bb % p, ("mli", hex(x), bb)
+            r, _ = self.run("add", a=ax, b=ay)
+            assert r < B and r % p == (x + y) % p, ("add", hex(x), hex(y))
+            r, _ = self.run("sub", a=ax, b=ay)
+            assert r < B and r % p == (x - y) % p, ("sub", hex(x), hex(y))
+            r, _ = self.run("neg", b=ax)
+            assert r < B and r % p == (-x) % p, ("neg", hex(x))
+            r, e = self.run("canon", a=ax)
+            assert r == x % p and e["lt"] == (1 if x < p else 0), ("canon", hex(x))
+        return True
+
+    # -- shared small pieces ------------------------------------------------
+    def _cond_sub_p(self, asm, v, want_flag=None):
+        """r = v - p if v >= p else v.  Returns regs; optionally writes (v < p) flag."""
+        L = self.L
+        pw = words(self.p, L)
+        t = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(t, v, pw, borrow_to=m)          # m = all-ones iff v < p
+        r = []
+        for k in range(L):
+            x, y, z = asm.tmp(), asm.tmp(), asm.tmp()
+            asm.logic("xor", x, t[k], v[k])
+            asm.logic("and", y, x, m)
+            asm.logic("xor", z, y, t[k])              # m ? v : t   (one LOP3 after ptxas)
+            r.append(z)
+        if want_flag is not None:
+            asm.logic("and", want_flag, m, 1)
+        return r
+
+
+class PseudoMersenne(Plan):
+    """2^n - c on L saturated limbs; stored values are any representative < 2^(32L)."""
+    family = "pseudo"
+
+    def __init__(self, prime):
+        super().__init__(prime)
+        n = prime.nbits
+        self.c = (1 << n) - prime.p
+        self.xs = 32 * self.L - n
+        self.fold = self.c << self.xs            # 2^(32L) == fold (mod p); cf. mm=m*2^xcess, pseudo.py:1594-1596
+        assert self.fold * (self.fold + 2) < (1 << 32), "fold constant too large for this plan"
+        assert self.bound <= 2 * self.p + self.fold + 1
+
+    def _fold_carry(self, asm, r, c, wide=False):
+        """r (L words) += c * fold, where c*2^(32L) was dropped.  c is a register.
+        wide=False needs c*fold < 2^32."""
+        L = self.L
+        o = asm.tmp(L)
+        c2 = asm.tmp()
+        if wide:
+            asm.madlo(o[0], c, self.fold, r[0], cout=True)
+            asm.madhi(o[1], c, self.fold, r[1], cin=True, cout=True)
+            start = 2
+        else:
+            asm.madlo(o[0], c, self.fold, r[0], cout=True)
+            start = 1
+        for k in range(start, L):
+            asm.add(o[k], r[k], 0, cin=True, cout=True)
+        asm.add(c2, 0, 0, cin=True)
+        # a second wrap leaves a tiny value, so this cannot carry (interpreter checks)
+        f = asm.tmp()
+        asm.madlo(f, c2, self.fold, o[0])
+        return [f] + o[1:]
+
+    def reduce_wide(self, asm, T):
+        """2L words -> L words: lo + fold*hi with two even/odd wide chains
+        (second_pass of pseudo.py:557-611 restated for a saturated radix)."""
+        L = self.L
+        lo, hi = T[:L], T[L:]
+        r = asm.tmp(L + 1)
+        cur = list(lo) + [0]
+        # even windows (0,1),(2,3).. take hi[0],hi[2]..; odd windows (1,2).. take hi[1],hi[3]..
+        ev = [(r[k], r[k + 1], hi[k], self.fold, cur[k], cur[k + 1]) for k in range(0, L, 2)]
+        asm.wide_chain(ev, last_carry_to=(r[L], 0) if L % 2 == 0 else None)
+        cur = list(r)
+        r2 = asm.tmp(L + 1)
+        od = [(r2[k], r2[k + 1], hi[k], self.fold, cur[k], cur[k + 1]) for k in range(1, L, 2)]
+        asm.wide_chain(od, last_carry_to=None)
+        res = [cur[0]] + r2[1:L + 1] if L % 2 == 0 else None
+        assert res is not None, "odd limb counts not needed yet"
+        return self._fold_carry(asm, res[:L], res[L])
+
+    def reduce_small(self, asm, T):
+        """L+1 words (top word < 2^32) -> L words."""
+        return self._fold_carry(asm, T[:self.L], T[self.L], wide=True)
+
+    def build_add(self):
+        asm = Asm(self.name + ".add")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        s = asm.tmp(L)
+        c = asm.tmp()
+        asm.add_chain(s, a, b, carry_to=(c, 0))
+        self._outs(asm, self._fold_carry(asm, s, c))
+        return asm
+
+    def build_sub(self, neg):
+        asm = Asm(self.name + (".neg" if neg else ".sub"))
+        L = self.L
+        if neg:
+            (b,) = self._io(asm, ["b"])
+            a = [0] * L
+        else:
+            a, b = self._io(asm, ["a", "b"])
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)           # value = d - 2^(32L)*[m]  == d - fold*[m]
+        f = asm.tmp()
+        asm.logic("and", f, m, self.fold)
+        e = asm.tmp(L)
+        m2 = asm.tmp()
+        asm.sub_chain(e, d, [f] + [0] * (L - 1), borrow_to=m2)
+        f2 = asm.tmp()
+        asm.logic("and", f2, m2, self.fold)
+        g = asm.tmp()
+        asm.sub(g, e[0], f2)                          # cannot borrow: e[0] >= 2^32 - fold here
+        self._outs(asm, [g] + e[1:])
+        return asm
+
+    def build_canon(self):
+        """Weak representative (< 2^(32L) <= 2p+fold+1) -> canonical residue; also
+        'lt' = 1 iff the input was already < p (modfsb's return, pseudo.py:272-283)."""
+        asm = Asm(self.name + ".canon")
+        (a,) = self._io(asm, ["a"])
+        lt = asm.tmp()
+        r = self._cond_sub_p(asm, a, want_flag=lt)
+        r = self._cond_sub_p(asm, r)
+        if self.bound > 3 * self.p:
+            r = self._cond_sub_p(asm, r)
+        self._outs(asm, r)
+        asm.out("lt", lt)
+        return asm
+
+
+class GenMersenne(Plan):
+    """p = 2^(2h) - 2^h - 1, h = 32*H (X448: H=7, L=14).  Stored values are any
+    representative < 2^(2h) (< 2p).  2^(2h) == 2^h + 1, so a double-length value
+    lo + 2^(2h)*(h0 + 2^h*h1) reduces to lo + (h0+h1) + 2^h*(h0 + 2*h1): additions of
+    half-length pieces only.  The reference reaches the same "no multiplies in the
+    reduction" through Montgomery form with shaped limbs (monty.py:258-298,597-627,
+    R = 2^476/2^504); applying the shape directly also removes nres/redc multiplies."""
+    family = "monty"
+
+    def __init__(self, prime):
+        super().__init__(prime)
+        n = prime.nbits
+        assert n % 64 == 0 and prime.p == (1 << n) - (1 << (n // 2)) - 1
+        self.H = self.L // 2
+
+    def _fold_top(self, asm, r, c, tail=None):
+        """r (L words) += c*(2^h + 1) for a dropped c*2^(2h); second wrap handled."""
+        L, H = self.L, self.H
+        o = asm.tmp(L)
+        c2 = asm.tmp()
+        for k in range(L):
+            asm.add(o[k], r[k], c if k in (0, H) else 0, cin=(k > 0), cout=True)
+        asm.add(c2, 0, 0, cin=True)
+        n2 = L if tail is None else tail
+        f = asm.tmp(n2)
+        for k in range(n2):
+            asm.add(f[k], o[k], c2 if k in (0, H) else 0, cin=(k > 0), cout=(k < n2 - 1))
+        return f + o[n2:]
+
+    def reduce_wide(self, asm, T):
+        L, H = self.L, self.H
+        lo, hi = T[:L], T[L:]
+        h0, h1 = hi[:H], hi[H:]
+        c = asm.tmp()
+        s1 = asm.tmp(L)
+        asm.add_chain(s1, lo, h0 + h0, carry_to=(c, 0))
+        s2 = asm.tmp(L)
+        c_b = asm.tmp()
+        asm.add_chain(s2, s1, h1 + h1, carry_to=(c_b, c))
+        s3 = asm.tmp(H)
+        c_c = asm.tmp()
+        asm.add_chain(s3, s2[H:], h1, carry_to=(c_c, c_b))
+        # after a wrap the value is < 4*(2^h+1): the second pass stops at word H
+        return self._fold_top(asm, s2[:H] + s3, c_c, tail=H + 1)
+
+    def reduce_small(self, asm, T):
+        return self._fold_top(asm, T[:self.L], T[self.L], tail=min(self.L, self.H + 2))
+
+    def build_add(self):
+        asm = Asm(self.name + ".add")
+        a, b = self._io(asm, ["a", "b"])
+        s = asm.tmp(self.L)
+        c = asm.tmp()
+        asm.add_chain(s, a, b, carry_to=(c, 0))
+        self._outs(asm, self._fold_top(asm, s, c, tail=self.H + 1))
+        return asm
+
+    def build_sub(self, neg):
+        asm = Asm(self.name + (".neg" if neg else ".sub"))
+        L, H = self.L, self.H
+        if neg:
+            (b,) = self._io(asm, ["b"])
+            a = [0] * L
+        else:
+            a, b = self._io(asm, ["a", "b"])
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)           # value = d - 2^(2h)*[m] == d - (2^h+1)*[m]
+        b1 = asm.tmp()
+        asm.logic("and", b1, m, 1)
+        e = asm.tmp(L)
+        m2 = asm.tmp()
+        asm.sub_chain(e, d, [b1 if k in (0, H) else 0 for k in range(L)], borrow_to=m2)
+        b2 = asm.tmp()
+        asm.logic("and", b2, m2, 1)
+        g = asm.tmp(L)
+        asm.sub_chain(g, e, [b2 if k in (0, H) else 0 for k in range(L)])   # e >= p here: no borrow
+        self._outs(asm, g)
+        return asm
+
+    def build_canon(self):
+        asm = Asm(self.name + ".canon")
+        (a,) = self._io(asm, ["a"])
+        lt = asm.tmp()
+        self._outs(asm, self._cond_sub_p(asm, a, want_flag=lt))
+        asm.out("lt", lt)
+        return asm
+
+
+def _naf_terms(x, nbits):
+    """Signed power-of-two terms of x (non-adjacent form), as [(bitpos, sign)]."""
+    out = []
+    k = 0
+    while x:
+        if x & 1:
+            s = 2 - (x & 3)           # +1 or -1
+            out.append((k, s))
+            x -= s
+        x >>= 1
+        k += 1
+    return out
+
+
+class Montgomery(Plan):
+    """Montgomery form with R = 2^(32L) for p == -1 (mod 2^32) whose complement
+    d = 2^(32L) - p is a short signed sum of powers of two (P-256: d = 2^224 - 2^192 -
+    2^96 + 1).  ndash = 1, the "Montgomery friendly" case of monty.py:740-751,
+    2242-2244.  Instead of L word-serial rounds (monty.py:663-872 interleaves one per
+    column) the whole quotient is produced at once:
+
+        Q = T_lo * d^-1 mod R            (d^-1 is sparse too: shifts and adds)
+        U = Q * d                        (shifts and adds; U_lo == T_lo by construction)
+        a*b*R^-1 = T_hi + Q - U_hi       (< 2p, one conditional subtraction)
+
+    so the reduction is ~60 add/sub-with-carry instructions on the ALU pipe and zero
+    multiplies.  Stored values are fully reduced, in [0, p): 32L == Nbits leaves no
+    spare bit for the reference's lazy "< 2p" results."""
+    family = "monty"
+
+    def __init__(self, prime):
+        super().__init__(prime)
+        L = self.L
+        assert prime.nbits == 32 * L and prime.p % (1 << 32) == (1 << 32) - 1
+        self.R = 1 << (32 * L)
+        self.bound = prime.p
+        self.d = self.R - prime.p
+        self.dinv = pow(self.d, -1, self.R)
+        self.d_terms = _naf_terms(self.d, 32 * L)
+        self.dinv_terms = _naf_terms(self.dinv, 32 * L)
+        assert len(self.d_terms) <= 8 and len(self.dinv_terms) <= 8, "modulus is not shaped"
+        self.R2 = self.R * self.R % prime.p           # nres constant (cw, monty.py:2246-2248)
+
+    def _shifted(self, asm, src, k, N):
+        """Words of (src << k) inside an N-word window: {index: reg}."""
+        w0, b = divmod(k, 32)
+        out = {}
+        n = len(src)
+        for j in range(n + (1 if b else 0)):
+            idx = w0 + j
+            if idx >= N:
+                break
+            if b == 0:
+                out[idx] = src[j]
+                continue
+            lo = src[j - 1] if j > 0 else None
+            hi = src[j] if j < n else None
+            d = asm.tmp()
+            if lo is None:
+                asm.shl(d, hi, b)
+            elif hi is None:
+                asm.shr(d, lo, 32 - b)
+            else:
+                asm.shfl(d, lo, hi, b)
+            out[idx] = d
+        return out
+
+    def _signed_sum(self, asm, src, terms, N, wrap_ok):
+        """sum of +-(src << k) over an N-word window; positives first so the running
+        value never goes negative when the exact result is non-negative."""
+        acc = None
+        for k, s in sorted(terms, key=lambda t: (-t[1], t[0])):
+            sh = self._shifted(asm, src, k, N)
+            if not sh:
+                continue
+            if acc is None:
+                assert s > 0
+                acc = [sh.get(i, 0) for i in range(N)]
+                continue
+            lo = min(sh)
+            new = asm.tmp(N - lo)
+            ops = [sh.get(i, 0) for i in range(lo, N)]
+            if s > 0:
+                asm.add_chain(new, acc[lo:], ops, wrap_ok=wrap_ok)
+            else:
+                asm.sub_chain(new, acc[lo:], ops, wrap_ok=wrap_ok)
+            acc = acc[:lo] + new
+        return acc
+
+    def _redc(self, asm, T):
+        """T: 2L words (< p*R) -> L words in [0,p)."""
+        L = self.L
+        lo, hi = T[:L], T[L:]
+        Q = self._signed_sum(asm, lo, self.dinv_terms, L, wrap_ok=True)
+        U = self._signed_sum(asm, Q, self.d_terms, 2 * L, wrap_ok=False)
+        m = asm.tmp(L + 1)
+        asm.add_chain(m[:L], hi, Q, carry_to=(m[L], 0))
+        n = asm.tmp(L + 1)
+        asm.sub_chain(n, m, U[L:] + [0])
+        return self._cond_sub_p9(asm, n)
+
+    def _cond_sub_p9(self, asm, v):
+        """v: L+1 words, < 2p  ->  L words in [0,p)."""
+        L = self.L
+        pw = words(self.p, L) + [0]
+        t = asm.tmp(L + 1)
+        m = asm.tmp()
+        asm.sub_chain(t, v, pw, borrow_to=m)
+        r = []
+        for k in range(L):
+            x, y, z = asm.tmp(), asm.tmp(), asm.tmp()
+            asm.logic("xor", x, t[k], v[k])
+            asm.logic("and", y, x, m)
+            asm.logic("xor", z, y, t[k])
+            r.append(z)
+        return r
+
+    def reduce_wide(self, asm, T):
+        return self._redc(asm, T)
+
+    def reduce_small(self, asm, T):
+        """L+1 words (a*b, b < 2^32; no R factor involved, monty.py:876-978) -> [0,p):
+        2^(32L) == d, so fold the top word through d's word-aligned terms until it fits."""
+        L = self.L
+        assert all(k % 32 == 0 for k, _ in self.d_terms)
+        cur, top = T[:L], T[L]
+        for _ in range(3):
+            w = self._signed_sum_top(asm, cur, top)
+            cur, top = w[:L], w[L]
+        # third fold cannot carry (interpreter checks via the final compare width)
+        return self._cond_sub_p9(asm, cur + [top])
+
+    def _signed_sum_top(self, asm, cur, c):
+        L = self.L
+        acc = list(cur) + [0]
+        for k, s in sorted(self.d_terms, key=lambda t: (-t[1], t[0])):
+            lo = k // 32
+            new = asm.tmp(L + 1 - lo)
+            ops = [c] + [0] * (L - lo)
+            if s > 0:
+                asm.add_chain(new, acc[lo:], ops)
+            else:
+                asm.sub_chain(new, acc[lo:], ops)
+            acc = acc[:lo] + new
+        return acc
+
+    def build_add(self):
+        asm = Asm(self.name + ".add")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        s = asm.tmp(L + 1)
+        asm.add_chain(s[:L], a, b, carry_to=(s[L], 0))
+        self._outs(asm, self._cond_sub_p9(asm, s))
+        return asm
+
+    def build_sub(self, neg):
+        asm = Asm(self.name + (".neg" if neg else ".sub"))
+        L = self.L
+        if neg:
+            (b,) = self._io(asm, ["b"])
+            a = [0] * L
+        else:
+            a, b = self._io(asm, ["a", "b"])
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)
+        pw = words(self.p, L)
+        pm = []
+        for k in range(L):
+            if pw[k] == 0:
+                pm.append(0)
+            elif pw[k] == M32:
+                pm.append(m)
+            else:
+                t = asm.tmp()
+                asm.logic("and", t, m, pw[k])
+                pm.append(t)
+        r = asm.tmp(L)
+        asm.add_chain(r, d, pm, wrap_ok=True)
+        self._outs(asm, r)
+        return asm
+
+    def build_canon(self):
+        """Stored values are already canonical; still performs the conditional subtraction
+        so that an out-of-range import (modimp of a value in [p, 2^(32L))) is handled here."""
+        asm = Asm(self.name + ".canon")
+        (a,) = self._io(asm, ["a"])
+        lt = asm.tmp()
+        self._outs(asm, self._cond_sub_p(asm, a, want_flag=lt))
+        asm.out("lt", lt)
+        return asm
+
+
+def make_plan(prime: Prime) -> Plan:
+    p, n = prime.p, prime.nbits
+    if n % 64 == 0 and p == (1 << n) - (1 << (n // 2)) - 1:
+        return GenMersenne(prime)
+    c = (1 << n) - p
+    L = (n + 31) // 32
+    if c < (1 << 12) and (c << (32 * L - n)) < (1 << 15):
+        return PseudoMersenne(prime)
+    return Montgomery(prime)

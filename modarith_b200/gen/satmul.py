@@ -1,0 +1,152 @@
+"""Full-width limb products for saturated radix-2^32 operands.
+
+The reference's product rows (`getZM`/`getZS`, pseudo.py:351-554; `getZMU`,
+monty.py:493-517) accumulate unsaturated limbs into a double-word `t` and
+mask/shift a limb out per column.  On sm_100a the multiplier is the 32-bit IMAD
+pipe and `IMAD.WIDE.U32.X` does a 32x32+64->64 multiply-accumulate with carry-in
+and carry-out in predicate registers, so the densest schedule is L*L wide
+products (L = ceil(Nbits/32) limbs, the algorithmic minimum of SURVEY.md
+section 8d) arranged so that every product lands on a 64-bit aligned accumulator
+window:
+
+  * products a[i]*b[j] with i+j even accumulate into the EVEN array E, whose
+    windows are words (0,1),(2,3),...;
+  * products with i+j odd accumulate into the ODD array O, windows (1,2),(3,4),...;
+  * within a row the windows are adjacent, so one carry chain ripples through the
+    row and its final carry is captured in the word above;
+  * E and O are merged once at the end with a single add-with-carry chain.
+
+All carry-capture words are shown (by the interpreter in ptx.py, which traps any
+lost carry) to hold only a few carry bits when they are written.
+"""
+from __future__ import annotations
+
+from .ptx import Asm
+
+
+class _Acc:
+    """Accumulator words that start as the literal 0 until first written."""
+
+    def __init__(self, asm: Asm, n: int):
+        self.asm = asm
+        self.reg = [asm.tmp() for _ in range(n)]
+        self.live = [False] * n
+
+    def src(self, k):
+        return self.reg[k] if self.live[k] else 0
+
+    def dst(self, k):
+        self.live[k] = True
+        return self.reg[k]
+
+
+def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
+    """prods: list of (s, a, b) with s ascending in steps of 2; window (s, s+1)."""
+    if not prods:
+        return
+    fresh = all(not acc.live[s] and not acc.live[s + 1] for s, _, _ in prods)
+    if fresh:
+        # untouched windows: independent wide multiplies, no carries can arise
+        for s, a, b in prods:
+            asm.mullo(acc.dst(s), a, b)
+            asm.mulhi(acc.dst(s + 1), a, b)
+        return
+    slots = []
+    for s, a, b in prods:
+        clo, chi = acc.src(s), acc.src(s + 1)
+        slots.append((acc.dst(s), acc.dst(s + 1), a, b, clo, chi))
+    top = prods[-1][0] + 2
+    if top < nwords:
+        c = acc.src(top)
+        asm.wide_chain(slots, last_carry_to=(acc.dst(top), c))
+    else:
+        asm.wide_chain(slots, last_carry_to=None)
+
+
+def _merge(asm: Asm, E: _Acc, O: _Acc, nwords):
+    """T = E + O as one carry chain; returns list of nwords regs/literals."""
+    T = []
+    started = False
+    for k in range(nwords):
+        e, o = E.src(k), O.src(k)
+        if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
+            # nothing to add yet (word 0 has no odd part): pass through
+            T.append(o if e == 0 else e)
+            continue
+        d = asm.tmp()
+        asm.add(d, e, o, cin=started, cout=(k < nwords - 1))
+        started = True
+        T.append(d)
+    return T
+
+
+def product(asm: Asm, a, b):
+    """Return the 2L words (registers) of a*b; a, b are lists of L register names."""
+    L = len(a)
+    assert len(b) == L
+    n = 2 * L
+    E, O = _Acc(asm, n), _Acc(asm, n)
+    for i in range(L):
+        ev = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 0]
+        od = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 1]
+        _row_chain(asm, E, ev, n)
+        _row_chain(asm, O, od, n)
+    return _merge(asm, E, O, n)
+
+
+def square(asm: Asm, a):
+    """Return the 2L words of a*a: 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum a_i^2 2^(64 i).
+
+    L(L-1)/2 off-diagonal wide products in even/odd chains, one funnel-shift
+    doubling pass on the ALU pipe, then the L diagonal squares added with one
+    wide carry chain: L(L+1)/2 wide products in total.
+    """
+    L = len(a)
+    n = 2 * L
+    E, O = _Acc(asm, n), _Acc(asm, n)
+    for i in range(L):
+        ev = [(i + j, a[i], a[j]) for j in range(i + 1, L) if (i + j) % 2 == 0]
+        od = [(i + j, a[i], a[j]) for j in range(i + 1, L) if (i + j) % 2 == 1]
+        _row_chain(asm, E, ev, n)
+        _row_chain(asm, O, od, n)
+    S = _merge(asm, E, O, n)            # off-diagonal sum, < 2^(64L-1)
+    # double: D[k] = (S[k] << 1) | (S[k-1] >> 31)
+    D = []
+    for k in range(n):
+        lo = S[k - 1] if k > 0 else 0
+        hi = S[k]
+        if isinstance(hi, int) and isinstance(lo, int):
+            D.append(0)
+            continue
+        d = asm.tmp()
+        if isinstance(lo, int):
+            asm.shl(d, hi, 1)
+        elif isinstance(hi, int):
+            asm.shr(d, lo, 31)
+        else:
+            asm.shfl(d, lo, hi, 1)
+        D.append(d)
+    # add the diagonal: window (2i, 2i+1) += a_i^2, one chain
+    T = [asm.tmp() for _ in range(n)]
+    slots = [(T[2 * i], T[2 * i + 1], a[i], a[i], D[2 * i], D[2 * i + 1]) for i in range(L)]
+    asm.wide_chain(slots, last_carry_to=None)
+    return T
+
+
+def times_small(asm: Asm, a, b):
+    """Return L+1 words of a*b for one 32-bit multiplier b (register or literal)."""
+    L = len(a)
+    lo = [asm.tmp() for _ in range(L)]
+    hi = [asm.tmp() for _ in range(L)]
+    for j in range(L):
+        asm.mullo(lo[j], a[j], b)
+        asm.mulhi(hi[j], a[j], b)
+    T = [lo[0]]
+    for k in range(1, L):
+        d = asm.tmp()
+        asm.add(d, lo[k], hi[k - 1], cin=(k > 1), cout=True)
+        T.append(d)
+    d = asm.tmp()
+    asm.add(d, hi[L - 1], 0, cin=True, cout=False)
+    T.append(d)
+    return T

@@ -1,0 +1,60 @@
+"""Named moduli and Montgomery-curve constants for the batched field / ladder path.
+
+Mirrors the "user editable area" tables of the reference generators
+(pseudo.py:1487-1550, monty.py:1961-2108) for the three moduli the hot path
+covers, and the curve constants of rfc7748.c:120-132.  Only data lives here;
+the limb plans are derived in gen/plan.py.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Prime:
+    name: str          # reference's prime name (argv[2] of pseudo.py / monty.py)
+    p: int
+    family: str        # "pseudo" (pseudo.py) or "monty" (monty.py) in the reference
+    # Montgomery-curve constants (rfc7748.c:120-132); None for field-only moduli
+    a24: int | None = None
+    cof: int | None = None
+    generator: int | None = None
+
+    @property
+    def nbits(self) -> int:
+        return self.p.bit_length()
+
+    @property
+    def nbytes(self) -> int:           # pseudo.py:1611-1614
+        return (self.nbits + 7) // 8
+
+    @property
+    def pm1d2(self) -> int:            # pseudo.py:1574-1579: 2-adicity of p-1
+        k, t = 0, self.p - 1
+        while t % 2 == 0:
+            k += 1
+            t >>= 1
+        return k
+
+    @property
+    def pe(self) -> int:               # pseudo.py:1580-1581: progenitor exponent
+        e = 1 << self.pm1d2
+        return (self.p - 1 - e) // (2 * e)
+
+    @property
+    def roi(self) -> int:              # pseudo.py:1616-1627: 2^k-th root of unity
+        k = self.pm1d2
+        p = self.p
+        if k == 1:
+            return p - 1
+        if k == 2:
+            return pow(2, (p - 1) // 4, p)
+        q = 2
+        while pow(q, (p - 1) // 2, p) == 1:
+            q += 1
+        return pow(q, (p - 1) >> k, p)
+
+
+X25519 = Prime("X25519", 2**255 - 19, "pseudo", a24=121665, cof=3, generator=9)
+X448 = Prime("X448", 2**448 - 2**224 - 1, "monty", a24=39081, cof=2, generator=5)
+NIST256 = Prime("NIST256", 2**256 - 2**224 + 2**192 + 2**96 - 1, "monty")
+
+PRIMES = {q.name: q for q in (X25519, X448, NIST256)}

@@ -1,0 +1,123 @@
+#!/usr/bin/env python3
+"""Build oracle/_ref: the reference's OWN 64-bit C for the hot path, compiled here.
+
+TEST INFRASTRUCTURE ONLY.  Runs the unmodified reference generators from
+/root/reference (read-only) inside a scratch directory, with three edits applied
+to SCRATCH COPIES of the scripts' module-level settings:
+
+  cyclescounter=False   libcpucycles is not installed (pseudo.py:29)
+  generic=False         what rfc7748.c:20 asks for (lazy add/sub, pseudo.py:1523-1528)
+  PSCR=False            plain mask-XOR cswap; removes the `static R` data race when
+                        the batch loop runs on many threads (pseudo.py:986-1005)
+
+and with oracle/addchain_standin.py on PATH as `addchain` (the Go tool is absent).
+The generated field.c is pasted into a scratch copy of rfc7748.c at its marker
+(rfc7748.c:24-28), `#define COUNT_CLOCKS` (rfc7748.c:30) is commented out, our
+ref_shim.c is appended, and the whole unit is compiled with gcc into
+
+  oracle/_ref/libref_X25519.so   pseudo.py 64 X25519  + rfc7748.c
+  oracle/_ref/libref_X448.so     monty.py  64 X448    + rfc7748.c
+  oracle/_ref/libref_NIST256.so  monty.py  64 NIST256 (generic=True: no ladder)
+
+Nothing from the reference is written into the repository outside oracle/_ref,
+which is git-ignored (it still travels to the GPU box with the snapshot).
+"""
+import os
+import re
+import shutil
+import stat
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("MODARITH_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+TARGETS = [
+    # (name, script, prime argument, generic flag, has rfc7748)
+    ("X25519", "pseudo.py", "X25519", False, True),
+    ("X448", "monty.py", "X448", False, True),
+    ("NIST256", "monty.py", "NIST256", True, False),
+]
+
+
+def _patch_settings(text, generic):
+    def sub(name, value, t):
+        new, n = re.subn(r"(?m)^%s=\w+" % name, "%s=%s" % (name, value), t, count=1)
+        assert n == 1, name
+        return new
+    text = sub("cyclescounter", "False", text)
+    text = sub("generic", "True" if generic else "False", text)
+    text = sub("PSCR", "False", text)
+    return text
+
+
+def build_one(name, script, prime, generic, ladder, cflags):
+    work = tempfile.mkdtemp(prefix="mab_ref_%s_" % name)
+    try:
+        bindir = os.path.join(work, "bin")
+        os.mkdir(bindir)
+        wrapper = os.path.join(bindir, "addchain")
+        with open(wrapper, "w") as f:
+            f.write("#!/bin/sh\nexec %s %s \"$@\"\n" % (sys.executable, os.path.join(HERE, "addchain_standin.py")))
+        os.chmod(wrapper, os.stat(wrapper).st_mode | stat.S_IEXEC)
+        gen = os.path.join(work, script)
+        with open(os.path.join(REF, script)) as f:
+            src = f.read()
+        with open(gen, "w") as f:
+            f.write(_patch_settings(src, generic))
+        env = dict(os.environ, PATH=bindir + os.pathsep + os.environ["PATH"])
+        r = subprocess.run([sys.executable, gen, "64", prime], cwd=work, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log = r.stdout
+        if "Passed - OK" not in log:
+            raise RuntimeError("reference generator self-test did not pass for %s:\n%s" % (name, log))
+        with open(os.path.join(work, "field.c")) as f:
+            field = f.read()
+        unit = field
+        if ladder:
+            with open(os.path.join(REF, "rfc7748.c")) as f:
+                drv = f.read()
+            drv = drv.replace("#define COUNT_CLOCKS", "//#define COUNT_CLOCKS", 1)
+            marker = "/*** Insert automatically generated code for modulus field.c here ***/"
+            assert marker in drv
+            unit = drv.replace(marker, marker + "\n" + field, 1)
+        with open(os.path.join(HERE, "ref_shim.c")) as f:
+            unit += "\n" + f.read()
+        os.makedirs(OUT, exist_ok=True)
+        csrc = os.path.join(OUT, "ref_%s.c" % name)
+        with open(csrc, "w") as f:
+            f.write(unit)
+        so = os.path.join(OUT, "libref_%s.so" % name)
+        cmd = ["gcc"] + cflags + ["-shared", "-fPIC", "-fopenmp", "-Dmain=ref_main", "-w"]
+        if ladder:
+            cmd.append("-DREF_HAS_RFC7748")
+        cmd += ["-o", so, csrc]
+        subprocess.check_call(cmd)
+        # the timing binary's checksums are golden vectors (pseudo.py:1862-1866)
+        timelog = ""
+        tbin = os.path.join(work, "time")
+        if os.path.exists(tbin) and os.environ.get("MODARITH_REF_TIME", "0") == "1":
+            timelog = subprocess.run([tbin], stdout=subprocess.PIPE, text=True).stdout
+        with open(os.path.join(OUT, "build_%s.log" % name), "w") as f:
+            f.write(log + "\n" + timelog)
+        return so
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def main():
+    if not os.path.isdir(REF):
+        print("reference tree %s not present: keeping any prebuilt oracle/_ref" % REF)
+        return 0
+    # x86-64-v3 (AVX2/BMI2/ADX-era) keeps the .so runnable on the GPU box's host
+    cflags = os.environ.get("MODARITH_REF_CFLAGS", "-O3 -march=x86-64-v3").split()
+    for t in TARGETS:
+        so = build_one(*t, cflags)
+        print("built", so)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,251 @@
+"""oracle/field_oracle.py -- CPU restatement of the reference's batch hot path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline leg of bench.py, never by the product package.
+
+Each function restates, on Python integers, the VALUE semantics of one generated
+function of the reference (pseudo.py / monty.py emit the same API for every
+modulus) or of the ladder driver rfc7748.c.  A field
+element is held as the integer it represents modulo p; the reference's
+unsaturated limbs, Montgomery factor R and lazily-reduced "< 2p" representatives
+are invisible after redc/modexp, which is the level parity is pinned at
+(SURVEY.md section 8c).  Where the reference's result depends on the
+representative (modshr on an unreduced value) the docstring says so.
+
+Pinned against: RFC 7748 vectors embedded in rfc7748.c:271,274 and
+simd/rfc7748_simt.cu:245,249, the deterministic outputs of rfc7748.c:main, the
+time.c checksums (pseudo.py:1862-1866), and oracle/_ref (the reference's own
+generated C compiled in this container) on random inputs -- see
+tests/test_oracle_pinned.py and tests/golden/.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from modarith_b200.primes import PRIMES, Prime  # noqa: E402  (data tables only)
+from modarith_b200 import addchain as _ac  # noqa: E402
+
+
+class FieldOracle:
+    """Value-level model of the 32-function generated API for one modulus."""
+
+    def __init__(self, prime: Prime | str):
+        self.P = PRIMES[prime] if isinstance(prime, str) else prime
+        self.p = self.P.p
+        self.nbytes = self.P.nbytes
+        self.k = self.P.pm1d2
+        self.pe = self.P.pe
+        self.roi = self.P.roi
+
+    # -- conversions ---------------------------------------------------------
+    def nres(self, m):
+        """pseudo.py:952-962 (copy) / monty.py:1386-1399 (multiply by R^2 mod p): value kept."""
+        return m % self.p
+
+    def redc(self, n):
+        """pseudo.py:965-976 / monty.py:1402-1416: canonical residue in [0,p)."""
+        return n % self.p
+
+    def modfsb(self, n):
+        """pseudo.py:272-283: n-=p, add back if negative; returns (value, 1 iff n was < p).
+        Defined for 0 <= n < 2p."""
+        return (n - self.p if n >= self.p else n), int(n < self.p)
+
+    # -- ring operations -----------------------------------------------------
+    def modadd(self, a, b):
+        """pseudo.py:286-304."""
+        return (a + b) % self.p
+
+    def modsub(self, a, b):
+        """pseudo.py:307-326."""
+        return (a - b) % self.p
+
+    def modneg(self, b):
+        """pseudo.py:329-348."""
+        return (-b) % self.p
+
+    def modmul(self, a, b):
+        """pseudo.py:616-659 / monty.py:663-872 (the R^-1 of Montgomery form cancels
+        against the nres of the operands)."""
+        return a * b % self.p
+
+    def modsqr(self, a):
+        """pseudo.py:663-702 / monty.py:982-1165."""
+        return a * a % self.p
+
+    def modmli(self, a, b: int):
+        """pseudo.py:705-728 / monty.py:876-978: plain small integer b >= 0, no R factor."""
+        assert b >= 0
+        return a * b % self.p
+
+    def modcpy(self, a):
+        """pseudo.py:730-743."""
+        return a
+
+    def modnsqr(self, a, n: int):
+        """pseudo.py:745-755: square n times."""
+        for _ in range(n):
+            a = a * a % self.p
+        return a
+
+    def modpro(self, w):
+        """pseudo.py:758-785: progenitor w^PE, PE=(p-1-2^k)/2^(k+1) (pseudo.py:1574-1581),
+        evaluated by the same straight-line sqr/mul program shape (our own chain)."""
+        return _ac.evaluate(_ac.find_chain(self.pe), w, self.p)
+
+    def modinv(self, x, h=None):
+        """pseudo.py:788-812 / monty.py:1225-1251.  0 -> 0."""
+        t = self.modpro(x) if h is None else h
+        s = x
+        for _ in range(self.k - 1):          # only when PM1D2 > 1
+            s = self.modsqr(s)
+            s = self.modmul(s, x)
+        t = self.modnsqr(t, self.k + 1)
+        return self.modmul(s, t)
+
+    def modis1(self, a):
+        """pseudo.py:877-891."""
+        return int(a % self.p == 1)
+
+    def modis0(self, a):
+        """pseudo.py:894-906."""
+        return int(a % self.p == 0)
+
+    def modzer(self):
+        """pseudo.py:909-919."""
+        return 0
+
+    def modone(self):
+        """pseudo.py:922-934."""
+        return 1
+
+    def modint(self, x: int):
+        """pseudo.py:937-949."""
+        return x % self.p
+
+    def modqr(self, h, x):
+        """pseudo.py:815-831: note the (h, x) argument order."""
+        r = self.modsqr(self.modpro(x)) if h is None else self.modsqr(h)
+        r = self.modmul(r, x)
+        if self.k > 1:
+            r = self.modnsqr(r, self.k - 1)
+        return self.modis1(r) | self.modis0(x)
+
+    def modsqrt(self, x, h=None):
+        """pseudo.py:834-874 / monty.py:1272-1311: x*x^PE when k=1; constant-time
+        Tonelli-Shanks with root of unity ROI (pseudo.py:1616-1630) when k>1.
+        Deterministic for non-residues as well."""
+        y = self.modpro(x) if h is None else h
+        s = self.modmul(y, x)
+        if self.k > 1:
+            t = self.modmul(s, y)
+            z = self.roi
+            for kk in range(self.k, 1, -1):
+                b = self.modnsqr(t, kk - 2)
+                d = 1 - self.modis1(b)
+                v = self.modmul(s, z)
+                s = v if d else s            # modcmv(d, v, s)
+                z = self.modsqr(z)
+                v = self.modmul(t, z)
+                t = v if d else t
+        return s
+
+    def modcsw(self, b, g, f):
+        """pseudo.py:979-1014."""
+        return (f, g) if b else (g, f)
+
+    def modcmv(self, b, g, f):
+        """pseudo.py:1017-1048: f <- g iff b."""
+        return g if b else f
+
+    def modshl(self, n, a):
+        """pseudo.py:1052-1065: raw left shift of the limb vector.  As a field value this
+        is a*2^n whenever the reference's limbs do not overflow."""
+        return (a << n) % self.p
+
+    def modshr(self, n, a):
+        """pseudo.py:1068-1081: raw right shift, returns the shifted-out bits.  Only pinned
+        for a canonical (redc'ed / modfsb'ed) input -- on an unreduced representative the
+        reference's result depends on which representative its radix happened to hold."""
+        a %= self.p
+        return a >> n, a & ((1 << n) - 1)
+
+    def modhaf(self, a):
+        """pseudo.py:1084-1100: a/2 mod p."""
+        a %= self.p
+        return (a >> 1) if a % 2 == 0 else ((a + self.p) >> 1)
+
+    def mod2r(self, r):
+        """pseudo.py:1102-1112 / monty.py:1568-1577: 2^r, or 0 when r >= 8*Nbytes."""
+        return 0 if r >= 8 * self.nbytes else (1 << r) % self.p
+
+    def modexp(self, a) -> bytes:
+        """pseudo.py:1115-1127: canonical value, big-endian, Nbytes."""
+        return (a % self.p).to_bytes(self.nbytes, "big")
+
+    def modimp(self, b: bytes):
+        """pseudo.py:1130-1146: big-endian Nbytes, one modfsb (so the integer must be < 2p
+        for the result to be a defined residue; any Nbytes string satisfies this for the
+        three moduli here except the 38 values >= 2p of X25519, which still land on the right
+        residue class); returns (value, 1 iff integer < p)."""
+        v = int.from_bytes(b, "big")
+        return v % self.p, int(v < self.p)
+
+    def modsign(self, a):
+        """pseudo.py:1149-1158."""
+        return (a % self.p) & 1
+
+    def modcmp(self, a, b):
+        """pseudo.py:1161-1174."""
+        return int((a - b) % self.p == 0)
+
+
+def rfc7748(prime: Prime | str, bk: bytes, bu: bytes) -> bytes:
+    """rfc7748.c:156-256 restated: bv = clamp(bk) * bu on the Montgomery curve, all
+    little-endian byte strings of Nbytes.  TWIST_SECURE branch (rfc7748.c:225-227)."""
+    F = FieldOracle(prime)
+    P = F.P
+    nb, nbits = P.nbytes, P.nbits
+    ck = bytearray(bk)
+    cu = bytearray(bu)[::-1]                      # reverse(): LE -> BE  (rfc7748.c:171)
+    r = nbits % 8 or 8
+    cu[0] &= (1 << r) - 1                         # mask()              (rfc7748.c:148-152,172)
+    s = (8 - nbits % 8) % 8                       # clamp()             (rfc7748.c:135-141)
+    ck[0] &= (-(1 << P.cof)) & 0xFF
+    ck[nb - 1] &= 0xFF >> s
+    ck[nb - 1] |= 0x80 >> s
+    u, _ = F.modimp(bytes(cu))                    # rfc7748.c:178
+    x1, x2, z2, x3, z3 = u, F.modone(), F.modzer(), u, F.modone()
+    swap = 0
+    for i in range(nbits - 1, -1, -1):            # rfc7748.c:186-221
+        kt = (ck[i // 8] >> (i % 8)) & 1
+        swap ^= kt
+        x2, x3 = F.modcsw(swap, x2, x3)
+        z2, z3 = F.modcsw(swap, z2, z3)
+        swap = kt
+        A = F.modadd(x2, z2)
+        C = F.modadd(x3, z3)
+        B = F.modsub(x2, z2)
+        D = F.modsub(x3, z3)
+        AA = F.modsqr(A)
+        BB = F.modsqr(B)
+        D = F.modmul(D, A)
+        C = F.modmul(C, B)
+        z3 = F.modsub(D, C)
+        E = F.modsub(AA, BB)
+        z2 = F.modmli(E, P.a24)
+        x3 = F.modadd(D, C)
+        z2 = F.modadd(z2, AA)
+        z2 = F.modmul(z2, E)
+        x3 = F.modsqr(x3)
+        z3 = F.modsqr(z3)
+        z3 = F.modmul(z3, x1)
+        x2 = F.modmul(AA, BB)
+    x2, x3 = F.modcsw(swap, x2, x3)
+    z2, z3 = F.modcsw(swap, z2, z3)
+    A = F.modpro(z2)                              # rfc7748.c:226-227
+    z2 = F.modinv(z2, A)
+    x2 = F.modmul(x2, z2)                         # rfc7748.c:252
+    return F.modexp(x2)[::-1]                     # rfc7748.c:254-255

@@ -1,0 +1,86 @@
+// tests/hostsim/hostsim.cpp -- TEST SCAFFOLDING ONLY (never part of the shipped library).
+//
+// Compiles the GENERATED field headers and the hand-written device templates
+// (mab_field.cuh, rfc7748_sm100.cuh) for the host with -DMAB_HOSTSIM, where every inline-PTX
+// block is replaced by its plain-C transcription (gen/ptx.py emit_sim).  The CPU test-suite
+// uses it to check the device-side logic against the oracle where there is no GPU; the GPU
+// tests then check the real PTX build through the C ABI.
+#define MAB_HOSTSIM 1
+#include <string.h>
+#include "gen/field_X25519.cuh"
+#include "gen/field_X448.cuh"
+#include "gen/field_NIST256.cuh"
+#include "rfc7748_sm100.cuh"
+
+enum SimOp {
+  S_ADD, S_SUB, S_NEG, S_MUL, S_SQR, S_MLI, S_NSQR, S_PRO, S_INV, S_INVH, S_QR, S_QRH, S_SQRT, S_SQRTH,
+  S_IS1, S_IS0, S_ONE, S_INT, S_NRES, S_REDC, S_CSW, S_CMV, S_SHL, S_SHR, S_HAF, S_2R, S_SIGN, S_CMP, S_FSB,
+  S_IMPW, S_EXPW
+};
+
+template <class F> static int sim_op(int op, const uint32_t* pa, const uint32_t* pb, uint32_t scalar, uint32_t* pr, uint32_t* pr2) {
+  constexpr int L = F::L;
+  typedef Field<F> Fd;
+  uint32_t a[L], b[L], r[L];
+  for (int i = 0; i < L; i++) { a[i] = pa ? pa[i] : 0; b[i] = pb ? pb[i] : 0; r[i] = 0; }
+  int ret = 0;
+  switch (op) {
+    case S_ADD: F::add(r, a, b); break;
+    case S_SUB: F::sub(r, a, b); break;
+    case S_NEG: F::neg(r, a); break;
+    case S_MUL: F::mul(r, a, b); break;
+    case S_SQR: F::sqr(r, a); break;
+    case S_MLI: F::mli(r, a, scalar); break;
+    case S_NSQR: Fd::cpy(r, a); Fd::nsqr(r, (int)scalar); break;
+    case S_PRO: F::pro(r, a); break;
+    case S_INV: Fd::template inv<false>(r, a, a); break;
+    case S_INVH: Fd::template inv<true>(r, a, b); break;
+    case S_QR: ret = (int)Fd::template qr<false>(a, a); break;
+    case S_QRH: ret = (int)Fd::template qr<true>(a, b); break;
+    case S_SQRT: Fd::template sqrt<false>(r, a, a); break;
+    case S_SQRTH: Fd::template sqrt<true>(r, a, b); break;
+    case S_IS1: ret = (int)Fd::is1(a); break;
+    case S_IS0: ret = (int)Fd::is0(a); break;
+    case S_ONE: Fd::one(r); break;
+    case S_INT: Fd::from_int(r, scalar); break;
+    case S_NRES: F::nres(r, a); break;
+    case S_REDC: Fd::to_words(r, a); break;
+    case S_CSW: Fd::csw(scalar & 1u, a, b); Fd::cpy(r, a); for (int i = 0; i < L; i++) pr2[i] = b[i]; break;
+    case S_CMV: Fd::cmv(scalar & 1u, a, b); Fd::cpy(r, b); break;
+    case S_SHL: Fd::cpy(r, a); Fd::shl(r, scalar); break;
+    case S_SHR: Fd::cpy(r, a); ret = (int)Fd::shr(r, scalar); break;
+    case S_HAF: Fd::cpy(r, a); Fd::haf(r); break;
+    case S_2R: Fd::pow2(r, scalar); break;
+    case S_SIGN: ret = (int)Fd::sign(a); break;
+    case S_CMP: ret = (int)Fd::cmp(a, b); break;
+    case S_FSB: Fd::cpy(r, a); ret = (int)Fd::fsb(r); break;
+    case S_IMPW: ret = (int)Fd::from_words(r, a); break;
+    case S_EXPW: Fd::to_words(r, a); break;
+    default: return -1;
+  }
+  for (int i = 0; i < L; i++) pr[i] = r[i];
+  return ret;
+}
+
+template <class F> static void sim_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) {
+  constexpr int L = F::L;
+  uint32_t k[L], u[L], out[L];
+  memcpy(k, bk, 4 * L);
+  memcpy(u, bu, 4 * L);
+  Rfc7748<F>::scalarmult(out, k, u);
+  memcpy(bv, out, 4 * L);
+}
+
+extern "C" {
+int sim_X25519_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X25519>(op, a, b, s, r, r2); }
+int sim_X448_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X448>(op, a, b, s, r, r2); }
+int sim_NIST256_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_NIST256>(op, a, b, s, r, r2); }
+void sim_X25519_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X25519>(bk, bu, bv); }
+void sim_X448_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X448>(bk, bu, bv); }
+void sim_X25519_rfc7748_batch(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, size_t n) {
+  for (size_t i = 0; i < n; i++) sim_rfc7748<F_X25519>(bk + 32 * i, bu + 32 * i, bv + 32 * i);
+}
+void sim_X448_rfc7748_batch(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, size_t n) {
+  for (size_t i = 0; i < n; i++) sim_rfc7748<F_X448>(bk + 56 * i, bu + 56 * i, bv + 56 * i);
+}
+}
