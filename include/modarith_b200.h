@@ -34,6 +34,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define MAB_API __attribute__((visibility("default")))
+#else
+#define MAB_API
+#endif
+
 #define MAB_X25519_LIMBS 8   /* Nlimbs  (pseudo.py:1404); Nbytes 32, Nbits 255 */
 #define MAB_X448_LIMBS 14    /*                           Nbytes 56, Nbits 448 */
 #define MAB_NIST256_LIMBS 8  /*                           Nbytes 32, Nbits 256 */
@@ -42,77 +48,77 @@ extern "C" {
 #define MAB_ERR_NODEVICE 100002
 
 /* ---- library-wide ---------------------------------------------------------------------- */
-const char *mab_version(void);
-const char *mab_error_string(int code);
-int mab_device_count(void);
+MAB_API const char *mab_version(void);
+MAB_API const char *mab_error_string(int code);
+MAB_API int mab_device_count(void);
 /* Parameters of a modulus by name ("X25519", ...): Wordlength/Nlimbs/Radix/Nbits/Nbytes macros
  * of the generated header (pseudo.py:1403-1407).  Returns 0, or MAB_ERR_BADARG. */
-int mab_params(const char *prime, int *wordlength, int *nlimbs, int *radix, int *nbits, int *nbytes);
+MAB_API int mab_params(const char *prime, int *wordlength, int *nlimbs, int *radix, int *nbits, int *nbytes);
 /* Algorithmic 32x32->64 limb products of one call, for roofline arithmetic:
  * what = "modmul" | "modsqr" | "modmli" | "modpro" | "modinv" | "modsqrt" | "rfc7748". */
-long long mab_products(const char *prime, const char *what);
+MAB_API long long mab_products(const char *prime, const char *what);
 
 /* INT32 multiplier-pipe microbenchmark: dependent-free streams of IMAD-class instructions.
  * variant 0: IMAD.WIDE.U32  1: IMAD.LO  2: IMAD.HI  3: IMAD.WIDE.U32.X carry chains
  *         4: IMAD.WIDE + 1 ALU op each  5: IMAD.WIDE + 2 ALU ops each  6: IADD3 only
  * Writes elapsed milliseconds and the number of multiply instructions executed by all threads. */
-int mab_imad_peak(int variant, int iters, int blocks, int threads, float *ms, double *instructions, void *stream);
+MAB_API int mab_imad_peak(int variant, int iters, int blocks, int threads, float *ms, double *instructions, void *stream);
 
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
   /* modfsb   pseudo.py:272-283   canonicalise in place; was_lt[i]=1 iff stored value was < p (may be NULL) */ \
-  int mab_##P##_modfsb(uint32_t *n_, int *was_lt, size_t n, size_t stride, void *stream);                 \
+  MAB_API int mab_##P##_modfsb(uint32_t *n_, int *was_lt, size_t n, size_t stride, void *stream);                 \
   /* modadd   pseudo.py:286-304 */                                                                        \
-  int mab_##P##_modadd(const uint32_t *a, const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modadd(const uint32_t *a, const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream); \
   /* modsub   pseudo.py:307-326 */                                                                        \
-  int mab_##P##_modsub(const uint32_t *a, const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modsub(const uint32_t *a, const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream); \
   /* modneg   pseudo.py:329-348 */                                                                        \
-  int mab_##P##_modneg(const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream);           \
+  MAB_API int mab_##P##_modneg(const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream);           \
   /* modmul   pseudo.py:616-659, monty.py:663-872 */                                                      \
-  int mab_##P##_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n, size_t stride, void *stream); \
   /* modsqr   pseudo.py:663-702, monty.py:982-1165 */                                                     \
-  int mab_##P##_modsqr(const uint32_t *a, uint32_t *c, size_t n, size_t stride, void *stream);            \
+  MAB_API int mab_##P##_modsqr(const uint32_t *a, uint32_t *c, size_t n, size_t stride, void *stream);            \
   /* modmli   pseudo.py:705-728, monty.py:876-978   0 <= b < 2^31 */                                      \
-  int mab_##P##_modmli(const uint32_t *a, int b, uint32_t *c, size_t n, size_t stride, void *stream);     \
+  MAB_API int mab_##P##_modmli(const uint32_t *a, int b, uint32_t *c, size_t n, size_t stride, void *stream);     \
   /* modcpy   pseudo.py:730-743 */                                                                        \
-  int mab_##P##_modcpy(const uint32_t *a, uint32_t *c, size_t n, size_t stride, void *stream);            \
+  MAB_API int mab_##P##_modcpy(const uint32_t *a, uint32_t *c, size_t n, size_t stride, void *stream);            \
   /* modnsqr  pseudo.py:745-755   square in place k times */                                              \
-  int mab_##P##_modnsqr(uint32_t *a, int k, size_t n, size_t stride, void *stream);                       \
+  MAB_API int mab_##P##_modnsqr(uint32_t *a, int k, size_t n, size_t stride, void *stream);                       \
   /* modpro   pseudo.py:758-785   z = w^((p-1-2^k)/2^(k+1)) */                                            \
-  int mab_##P##_modpro(const uint32_t *w, uint32_t *z, size_t n, size_t stride, void *stream);            \
+  MAB_API int mab_##P##_modpro(const uint32_t *w, uint32_t *z, size_t n, size_t stride, void *stream);            \
   /* modinv   pseudo.py:788-812   h = progenitor planes or NULL; 0 -> 0 */                                \
-  int mab_##P##_modinv(const uint32_t *x, const uint32_t *h, uint32_t *z, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modinv(const uint32_t *x, const uint32_t *h, uint32_t *z, size_t n, size_t stride, void *stream); \
   /* modqr    pseudo.py:815-831   note (h, x) order; out[i] = 1 iff x is a QR or 0 */                     \
-  int mab_##P##_modqr(const uint32_t *h, const uint32_t *x, int *out, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modqr(const uint32_t *h, const uint32_t *x, int *out, size_t n, size_t stride, void *stream); \
   /* modsqrt  pseudo.py:834-874 */                                                                        \
-  int mab_##P##_modsqrt(const uint32_t *x, const uint32_t *h, uint32_t *r, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modsqrt(const uint32_t *x, const uint32_t *h, uint32_t *r, size_t n, size_t stride, void *stream); \
   /* modis1 / modis0  pseudo.py:877-906 */                                                                \
-  int mab_##P##_modis1(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);               \
-  int mab_##P##_modis0(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);               \
+  MAB_API int mab_##P##_modis1(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);               \
+  MAB_API int mab_##P##_modis0(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);               \
   /* modzer / modone / modint  pseudo.py:909-949 */                                                       \
-  int mab_##P##_modzer(uint32_t *a, size_t n, size_t stride, void *stream);                               \
-  int mab_##P##_modone(uint32_t *a, size_t n, size_t stride, void *stream);                               \
-  int mab_##P##_modint(int x, uint32_t *a, size_t n, size_t stride, void *stream);                        \
+  MAB_API int mab_##P##_modzer(uint32_t *a, size_t n, size_t stride, void *stream);                               \
+  MAB_API int mab_##P##_modone(uint32_t *a, size_t n, size_t stride, void *stream);                               \
+  MAB_API int mab_##P##_modint(int x, uint32_t *a, size_t n, size_t stride, void *stream);                        \
   /* nres / redc  pseudo.py:952-976, monty.py:1386-1416.  Plain side = canonical value as           */    \
   /* MAB_<P>_LIMBS little-endian 32-bit words (planes).                                              */    \
-  int mab_##P##_nres(const uint32_t *m, uint32_t *n_, size_t n, size_t stride, void *stream);             \
-  int mab_##P##_redc(const uint32_t *n_, uint32_t *m, size_t n, size_t stride, void *stream);             \
+  MAB_API int mab_##P##_nres(const uint32_t *m, uint32_t *n_, size_t n, size_t stride, void *stream);             \
+  MAB_API int mab_##P##_redc(const uint32_t *n_, uint32_t *m, size_t n, size_t stride, void *stream);             \
   /* modcsw / modcmv  pseudo.py:979-1048   b[i] in {0,1} per element */                                   \
-  int mab_##P##_modcsw(const int *b, uint32_t *g, uint32_t *f, size_t n, size_t stride, void *stream);    \
-  int mab_##P##_modcmv(const int *b, const uint32_t *g, uint32_t *f, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modcsw(const int *b, uint32_t *g, uint32_t *f, size_t n, size_t stride, void *stream);    \
+  MAB_API int mab_##P##_modcmv(const int *b, const uint32_t *g, uint32_t *f, size_t n, size_t stride, void *stream); \
   /* modshl / modshr  pseudo.py:1052-1081   k < 32; see DESIGN.md for the saturated-limb semantics */     \
-  int mab_##P##_modshl(unsigned int k, uint32_t *a, size_t n, size_t stride, void *stream);               \
-  int mab_##P##_modshr(unsigned int k, uint32_t *a, int *out, size_t n, size_t stride, void *stream);     \
+  MAB_API int mab_##P##_modshl(unsigned int k, uint32_t *a, size_t n, size_t stride, void *stream);               \
+  MAB_API int mab_##P##_modshr(unsigned int k, uint32_t *a, int *out, size_t n, size_t stride, void *stream);     \
   /* modhaf   pseudo.py:1084-1100;  mod2r  pseudo.py:1102-1112 */                                         \
-  int mab_##P##_modhaf(uint32_t *a, size_t n, size_t stride, void *stream);                               \
-  int mab_##P##_mod2r(unsigned int r, uint32_t *a, size_t n, size_t stride, void *stream);                \
+  MAB_API int mab_##P##_modhaf(uint32_t *a, size_t n, size_t stride, void *stream);                               \
+  MAB_API int mab_##P##_mod2r(unsigned int r, uint32_t *a, size_t n, size_t stride, void *stream);                \
   /* modexp   pseudo.py:1115-1127   canonical big-endian Nbytes per element */                            \
-  int mab_##P##_modexp(const uint32_t *a, char *b, size_t n, size_t stride, void *stream);                \
+  MAB_API int mab_##P##_modexp(const uint32_t *a, char *b, size_t n, size_t stride, void *stream);                \
   /* modimp   pseudo.py:1130-1146   status[i] = 1 iff the integer was < p (status may be NULL) */         \
-  int mab_##P##_modimp(const char *b, uint32_t *a, int *status, size_t n, size_t stride, void *stream);   \
+  MAB_API int mab_##P##_modimp(const char *b, uint32_t *a, int *status, size_t n, size_t stride, void *stream);   \
   /* modsign / modcmp  pseudo.py:1149-1174 */                                                             \
-  int mab_##P##_modsign(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);              \
-  int mab_##P##_modcmp(const uint32_t *a, const uint32_t *b, int *out, size_t n, size_t stride, void *stream);
+  MAB_API int mab_##P##_modsign(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);              \
+  MAB_API int mab_##P##_modcmp(const uint32_t *a, const uint32_t *b, int *out, size_t n, size_t stride, void *stream);
 
 MAB_DECLARE_FIELD(X25519)
 MAB_DECLARE_FIELD(X448)
@@ -120,13 +126,13 @@ MAB_DECLARE_FIELD(NIST256)
 
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */
-int mab_X25519_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
-int mab_X448_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
+MAB_API int mab_X25519_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
+MAB_API int mab_X448_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
 /* Same with HOST pointers: copies in, runs on `device`, copies out, returns when bv is complete.
  * Chunked over three streams so transfers overlap the ladder; pinned memory is used at full
  * speed, pageable memory works but serialises the copies. */
-int mab_X25519_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
-int mab_X448_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
+MAB_API int mab_X25519_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
+MAB_API int mab_X448_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
 
 #ifdef __cplusplus
 }

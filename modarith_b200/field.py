@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference's generated-code API, batched on one B200.
+
+    F = Field("X25519")
+    x = F.modimp(bytes_be)            # [n, Nbytes] uint8 cuda tensor -> limb planes
+    F.modmul(x, y, z)                 # same names / argument order as the generated C
+    out = F.modexp(z)                 # canonical big-endian bytes
+
+Every method forwards to one `mab_<PRIME>_<function>` entry point of the C ABI
+(include/modarith_b200.h) on the current torch CUDA stream.  torch is used only to own
+device memory and streams.  A batch of n field elements is an int32 tensor of shape
+[Nlimbs, n] on the GPU ("limb planes": plane j holds limb j of every element), opaque like
+the reference's spint[Nlimbs]; outputs may alias inputs exactly as in the reference
+(pseudo.py:1832-1845).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as _lib
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Field:
+    def __init__(self, prime: str, device=None):
+        if prime not in _lib.PRIMES:
+            raise ValueError("unsupported modulus %r (have %s)" % (prime, ", ".join(_lib.PRIMES)))
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MabError("modarith_b200 needs a CUDA device: there is no CPU fallback")
+        self.prime = prime
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        par = _lib.params(prime)
+        self.Wordlength, self.Nlimbs, self.Radix = par["wordlength"], par["nlimbs"], par["radix"]
+        self.Nbits, self.Nbytes = par["nbits"], par["nbytes"]
+
+    # -- memory ----------------------------------------------------------------------------
+    def alloc(self, n: int) -> torch.Tensor:
+        return torch.empty((self.Nlimbs, n), dtype=torch.int32, device=self.device)
+
+    def _ints(self, n):
+        return torch.empty((n,), dtype=torch.int32, device=self.device)
+
+    def _call(self, name, lead, planes):
+        """planes: a tensor defining n/stride."""
+        assert planes.dtype == torch.int32 and planes.dim() == 2 and planes.shape[0] == self.Nlimbs
+        assert planes.stride(1) == 1, "limb planes must be contiguous along the element axis"
+        n, stride = planes.shape[1], planes.stride(0) if planes.shape[1] > 0 else 0
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        fn = getattr(self.lib, "mab_%s_%s" % (self.prime, name))
+        with torch.cuda.device(self.device):
+            _lib.check(fn(*lead, n, max(stride, n), stream), "mab_%s_%s" % (self.prime, name))
+
+    def _chk(self, *ts):
+        ref = None
+        for t in ts:
+            if t is None:
+                continue
+            assert t.is_cuda and t.dtype == torch.int32 and t.dim() == 2 and t.shape[0] == self.Nlimbs, \
+                "expected int32 limb planes [Nlimbs, n] on the GPU"
+            if ref is None:
+                ref = t
+            else:
+                assert t.shape == ref.shape and t.stride() == ref.stride(), "operands must share shape and pitch"
+        return ref
+
+    # -- the generated-code API (reference argument order) ------------------------------------
+    def modfsb(self, n_):
+        out = self._ints(n_.shape[1])
+        self._call("modfsb", [_ptr(n_), _ptr(out)], self._chk(n_))
+        return out
+
+    def modadd(self, a, b, n_):
+        self._call("modadd", [_ptr(a), _ptr(b), _ptr(n_)], self._chk(a, b, n_))
+
+    def modsub(self, a, b, n_):
+        self._call("modsub", [_ptr(a), _ptr(b), _ptr(n_)], self._chk(a, b, n_))
+
+    def modneg(self, b, n_):
+        self._call("modneg", [_ptr(b), _ptr(n_)], self._chk(b, n_))
+
+    def modmul(self, a, b, c):
+        self._call("modmul", [_ptr(a), _ptr(b), _ptr(c)], self._chk(a, b, c))
+
+    def modsqr(self, a, c):
+        self._call("modsqr", [_ptr(a), _ptr(c)], self._chk(a, c))
+
+    def modmli(self, a, b: int, c):
+        self._call("modmli", [_ptr(a), int(b), _ptr(c)], self._chk(a, c))
+
+    def modcpy(self, a, c):
+        self._call("modcpy", [_ptr(a), _ptr(c)], self._chk(a, c))
+
+    def modnsqr(self, a, n: int):
+        self._call("modnsqr", [_ptr(a), int(n)], self._chk(a))
+
+    def modpro(self, w, z):
+        self._call("modpro", [_ptr(w), _ptr(z)], self._chk(w, z))
+
+    def modinv(self, x, h, z):
+        self._call("modinv", [_ptr(x), _ptr(h), _ptr(z)], self._chk(x, h, z))
+
+    def modqr(self, h, x):
+        out = self._ints(x.shape[1])
+        self._call("modqr", [_ptr(h), _ptr(x), _ptr(out)], self._chk(x, h))
+        return out
+
+    def modsqrt(self, x, h, r):
+        self._call("modsqrt", [_ptr(x), _ptr(h), _ptr(r)], self._chk(x, h, r))
+
+    def modis1(self, a):
+        out = self._ints(a.shape[1])
+        self._call("modis1", [_ptr(a), _ptr(out)], self._chk(a))
+        return out
+
+    def modis0(self, a):
+        out = self._ints(a.shape[1])
+        self._call("modis0", [_ptr(a), _ptr(out)], self._chk(a))
+        return out
+
+    def modzer(self, a):
+        self._call("modzer", [_ptr(a)], self._chk(a))
+
+    def modone(self, a):
+        self._call("modone", [_ptr(a)], self._chk(a))
+
+    def modint(self, x: int, a):
+        self._call("modint", [int(x), _ptr(a)], self._chk(a))
+
+    def nres(self, m, n_):
+        self._call("nres", [_ptr(m), _ptr(n_)], self._chk(m, n_))
+
+    def redc(self, n_, m):
+        self._call("redc", [_ptr(n_), _ptr(m)], self._chk(n_, m))
+
+    def modcsw(self, b, g, f):
+        assert b.dtype == torch.int32 and b.shape == (g.shape[1],)
+        self._call("modcsw", [_ptr(b), _ptr(g), _ptr(f)], self._chk(g, f))
+
+    def modcmv(self, b, g, f):
+        assert b.dtype == torch.int32 and b.shape == (g.shape[1],)
+        self._call("modcmv", [_ptr(b), _ptr(g), _ptr(f)], self._chk(g, f))
+
+    def modshl(self, n: int, a):
+        self._call("modshl", [int(n), _ptr(a)], self._chk(a))
+
+    def modshr(self, n: int, a):
+        out = self._ints(a.shape[1])
+        self._call("modshr", [int(n), _ptr(a), _ptr(out)], self._chk(a))
+        return out
+
+    def modhaf(self, a):
+        self._call("modhaf", [_ptr(a)], self._chk(a))
+
+    def mod2r(self, r: int, a):
+        self._call("mod2r", [int(r), _ptr(a)], self._chk(a))
+
+    def modexp(self, a, b=None):
+        n = a.shape[1]
+        if b is None:
+            b = torch.empty((n, self.Nbytes), dtype=torch.uint8, device=self.device)
+        assert b.is_contiguous() and b.shape == (n, self.Nbytes) and b.dtype == torch.uint8
+        self._call("modexp", [_ptr(a), _ptr(b)], self._chk(a))
+        return b
+
+    def modimp(self, b, a=None):
+        """b: [n, Nbytes] uint8 big-endian.  Returns (planes, status) with status[i]=1 iff < p."""
+        assert b.is_cuda and b.dtype == torch.uint8 and b.dim() == 2 and b.shape[1] == self.Nbytes and b.is_contiguous()
+        n = b.shape[0]
+        if a is None:
+            a = self.alloc(n)
+        st = self._ints(n)
+        self._call("modimp", [_ptr(b), _ptr(a), _ptr(st)], self._chk(a))
+        return a, st
+
+    def modsign(self, a):
+        out = self._ints(a.shape[1])
+        self._call("modsign", [_ptr(a), _ptr(out)], self._chk(a))
+        return out
+
+    def modcmp(self, a, b):
+        out = self._ints(a.shape[1])
+        self._call("modcmp", [_ptr(a), _ptr(b), _ptr(out)], self._chk(a, b))
+        return out
+
+    # -- conveniences for tests / small batches ------------------------------------------------
+    def from_ints(self, values):
+        """Python integers (< 2^(8*Nbytes)) -> planes via modimp."""
+        import numpy as np
+        raw = b"".join(int(v).to_bytes(self.Nbytes, "big") for v in values)
+        b = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).reshape(len(values), self.Nbytes).copy()).to(self.device)
+        return self.modimp(b)[0]
+
+    def to_ints(self, a):
+        b = self.modexp(a).cpu().numpy()
+        return [int.from_bytes(b[i].tobytes(), "big") for i in range(b.shape[0])]

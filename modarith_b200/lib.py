@@ -1,0 +1,120 @@
+"""ctypes binding of libmodarith_b200.so (include/modarith_b200.h).
+
+The reference binds its generated functions the same way (ctypes.CDLL on test.so,
+pseudo.py:1704-1750).  There is NO CPU fallback: if the CUDA library has not been built
+(python -m modarith_b200.build) or cannot be loaded, importing a field raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_size_t, c_uint, c_void_p, POINTER, c_float, c_double, c_longlong
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(PKG, "libmodarith_b200.so")
+
+PRIMES = ("X25519", "X448", "NIST256")
+CURVES = ("X25519", "X448")
+
+_P = c_void_p          # device pointers travel as integers
+_TAIL = [c_size_t, c_size_t, c_void_p]      # n, stride, stream
+
+# name -> leading argument types (the reference's argument order), SURVEY.md 8a
+FIELD_SIGNATURES = {
+    "modfsb": [_P, _P],
+    "modadd": [_P, _P, _P],
+    "modsub": [_P, _P, _P],
+    "modneg": [_P, _P],
+    "modmul": [_P, _P, _P],
+    "modsqr": [_P, _P],
+    "modmli": [_P, c_int, _P],
+    "modcpy": [_P, _P],
+    "modnsqr": [_P, c_int],
+    "modpro": [_P, _P],
+    "modinv": [_P, _P, _P],
+    "modqr": [_P, _P, _P],
+    "modsqrt": [_P, _P, _P],
+    "modis1": [_P, _P],
+    "modis0": [_P, _P],
+    "modzer": [_P],
+    "modone": [_P],
+    "modint": [c_int, _P],
+    "nres": [_P, _P],
+    "redc": [_P, _P],
+    "modcsw": [_P, _P, _P],
+    "modcmv": [_P, _P, _P],
+    "modshl": [c_uint, _P],
+    "modshr": [c_uint, _P, _P],
+    "modhaf": [_P],
+    "mod2r": [c_uint, _P],
+    "modexp": [_P, _P],
+    "modimp": [_P, _P, _P],
+    "modsign": [_P, _P],
+    "modcmp": [_P, _P, _P],
+}
+
+_lib = None
+
+
+class MabError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library, binding every symbol the header declares.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise MabError("%s is missing: build it with `python -m modarith_b200.build` "
+                       "(nvcc, sm_100a).  There is no CPU fallback." % LIBPATH)
+    lib = ctypes.CDLL(LIBPATH)
+    lib.mab_version.restype = c_char_p
+    lib.mab_error_string.restype = c_char_p
+    lib.mab_error_string.argtypes = [c_int]
+    lib.mab_device_count.restype = c_int
+    lib.mab_params.argtypes = [c_char_p] + [POINTER(c_int)] * 5
+    lib.mab_products.argtypes = [c_char_p, c_char_p]
+    lib.mab_products.restype = c_longlong
+    lib.mab_imad_peak.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_double), c_void_p]
+    for P in PRIMES:
+        for name, lead in FIELD_SIGNATURES.items():
+            fn = getattr(lib, "mab_%s_%s" % (P, name))
+            fn.argtypes = lead + _TAIL
+            fn.restype = c_int
+    for P in CURVES:
+        fn = getattr(lib, "mab_%s_rfc7748" % P)
+        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
+        fn.restype = c_int
+        fn = getattr(lib, "mab_%s_rfc7748_host" % P)
+        fn.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int]
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Every symbol include/modarith_b200.h declares (used by the CPU-side ABI test)."""
+    syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak"]
+    for P in PRIMES:
+        syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
+    for P in CURVES:
+        syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P]
+    return syms
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        msg = load().mab_error_string(code).decode()
+        raise MabError("%s failed: %s (code %d)" % (what or "modarith_b200 call", msg, code))
+
+
+def params(prime: str):
+    lib = load()
+    v = [c_int() for _ in range(5)]
+    check(lib.mab_params(prime.encode(), *[ctypes.byref(x) for x in v]), "mab_params")
+    return dict(zip(("wordlength", "nlimbs", "radix", "nbits", "nbytes"), [x.value for x in v]))
+
+
+def products(prime: str, what: str) -> int:
+    return int(load().mab_products(prime.encode(), what.encode()))

@@ -15,9 +15,11 @@ The generated field.c is pasted into a scratch copy of rfc7748.c at its marker
 (rfc7748.c:24-28), `#define COUNT_CLOCKS` (rfc7748.c:30) is commented out, our
 ref_shim.c is appended, and the whole unit is compiled with gcc into
 
-  oracle/_ref/libref_X25519.so   pseudo.py 64 X25519  + rfc7748.c
-  oracle/_ref/libref_X448.so     monty.py  64 X448    + rfc7748.c
-  oracle/_ref/libref_NIST256.so  monty.py  64 NIST256 (generic=True: no ladder)
+  oracle/_ref/libref_X25519.so          pseudo.py 64 X25519  + rfc7748.c   (generic=False)
+  oracle/_ref/libref_X448.so            monty.py  64 X448    + rfc7748.c   (generic=False)
+  oracle/_ref/libref_X25519_generic.so  pseudo.py 64 X25519  field only    (generic=True)
+  oracle/_ref/libref_X448_generic.so    monty.py  64 X448    field only    (generic=True)
+  oracle/_ref/libref_NIST256.so         monty.py  64 NIST256 field only    (generic=True)
 
 Nothing from the reference is written into the repository outside oracle/_ref,
 which is git-ignored (it still travels to the GPU box with the snapshot).
@@ -36,8 +38,12 @@ OUT = os.path.join(HERE, "_ref")
 
 TARGETS = [
     # (name, script, prime argument, generic flag, has rfc7748)
-    ("X25519", "pseudo.py", "X25519", False, True),
+    ("X25519", "pseudo.py", "X25519", False, True),          # ladder build: lazy add/sub
     ("X448", "monty.py", "X448", False, True),
+    # field builds (generic=True, the scripts' default): modadd/modsub reduce to < 2p, so a
+    # single modexp after them is canonical -- these back the field-level golden vectors
+    ("X25519_generic", "pseudo.py", "X25519", True, False),
+    ("X448_generic", "monty.py", "X448", True, False),
     ("NIST256", "monty.py", "NIST256", True, False),
 ]
 

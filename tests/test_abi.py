@@ -1,0 +1,71 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol
+include/modarith_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from modarith_b200 import lib as mlib
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from modarith_b200 import build
+    return build.build(verbose=False)
+
+
+def header_symbols():
+    h = open(os.path.join(ROOT, "include", "modarith_b200.h")).read()
+    syms = set(re.findall(r"\b(mab_[a-z0-9_]+)\s*\(", h))
+    macro = re.findall(r"mab_##P##_([a-z0-9]+)\s*\(", h)
+    for P in ("X25519", "X448", "NIST256"):
+        syms |= {"mab_%s_%s" % (P, m) for m in macro}
+    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host)?)\s*\(", h))
+    return syms
+
+
+def test_library_exports_every_declared_symbol(built):
+    dll = ctypes.CDLL(built)
+    want = header_symbols()
+    assert len(want) == 6 + 3 * 30 + 4
+    for s in sorted(want):
+        assert hasattr(dll, s), s
+    assert want == set(mlib.exported_symbols())
+
+
+def test_loader_binds_and_reports(built):
+    l = mlib.load()
+    assert b"sm_100a" in l.mab_version()
+    assert mlib.params("X25519") == {"wordlength": 32, "nlimbs": 8, "radix": 32, "nbits": 255, "nbytes": 32}
+    assert mlib.params("X448")["nlimbs"] == 14 and mlib.params("NIST256")["nbytes"] == 32
+    # SURVEY.md 8d work counts with this build's chains (251S+13M, 445S+14M)
+    assert mlib.products("X25519", "modmul") == 64 and mlib.products("X25519", "modsqr") == 36
+    assert mlib.products("X448", "modmul") == 196 and mlib.products("X448", "modsqr") == 105
+    assert mlib.products("X25519", "rfc7748") == 255 * (5 * 64 + 4 * 36 + 8) + 251 * 36 + 13 * 64 + (36 + 64 + 3 * 36 + 64) + 64
+    assert mlib.products("NIST256", "rfc7748") == -1
+    assert l.mab_error_string(mlib.load().mab_params(b"nope", None, None, None, None, None)) == b"modarith_b200: bad argument"
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the product path refuses to run instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from modarith_b200 import Field, x25519
+    import numpy as np
+    with pytest.raises(mlib.MabError):
+        Field("X25519")
+    with pytest.raises(mlib.MabError):
+        x25519(np.zeros((1, 32), np.uint8), np.zeros((1, 32), np.uint8))
+
+
+def test_product_package_never_imports_the_oracle():
+    for dp, _, fns in os.walk(os.path.join(ROOT, "modarith_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".inc")):
+                text = open(os.path.join(dp, fn)).read()
+                assert "field_oracle" not in text and "oracle/" not in text.replace("oracle/_ref", "").replace(
+                    "oracle/build_ref", "").replace("oracle/addchain", ""), os.path.join(dp, fn)

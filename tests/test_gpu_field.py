@@ -1,0 +1,219 @@
+"""Parity of the batched field API (C ABI, limb planes on the GPU) with the oracle, the golden
+vectors produced by the reference's generated C, and oracle/_ref at larger sizes."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from field_oracle import FieldOracle
+from modarith_b200.primes import PRIMES
+import util
+
+pytestmark = pytest.mark.gpu
+NAMES = list(PRIMES)
+
+
+def _field(name):
+    from modarith_b200 import Field
+    return Field(name)
+
+
+def _bytes(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_field_golden(golden_field, name):
+    g = golden_field[name]
+    F = _field(name)
+    nb = g["nbytes"]
+    a = torch.from_numpy(np.frombuffer(bytes.fromhex("".join(g["a"])), dtype=np.uint8).reshape(-1, nb).copy()).cuda()
+    b = torch.from_numpy(np.frombuffer(bytes.fromhex("".join(g["b"])), dtype=np.uint8).reshape(-1, nb).copy()).cuda()
+    x, st = F.modimp(a)
+    y, _ = F.modimp(b)
+    assert st.cpu().tolist() == g["ops"]["id"]["status"]
+    n = x.shape[1]
+    r = F.alloc(n)
+
+    def check(op):
+        out = _bytes(F.modexp(r))
+        got = [out[i].tobytes().hex() for i in range(n)]
+        assert got == g["ops"][op]["out"], (name, op)
+
+    F.modmul(x, y, r); check("mul")
+    F.modsqr(x, r); check("sqr")
+    F.modinv(x, None, r); check("inv")
+    F.modsqrt(x, None, r); check("sqrt")
+    F.modadd(x, y, r); check("add")
+    F.modsub(x, y, r); check("sub")
+    F.modneg(x, r); check("neg")
+    F.modpro(x, r); check("pro")
+    F.modcpy(x, r); check("id")
+    F.modmli(x, g["mli_int"], r); check("mli")
+    F.modcpy(x, r); F.modhaf(r); check("haf")
+    assert F.modqr(None, x).cpu().tolist() == g["ops"]["qr"]["status"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_every_api_function_vs_oracle(name):
+    F = _field(name)
+    O = FieldOracle(name)
+    p = O.p
+    rng = random.Random(2)
+    xs = [0, 1, 2, p - 1, p - 2, (p + 1) // 2, 4, 9] + [rng.randrange(p) for _ in range(200)]
+    ys = [rng.randrange(p) for _ in xs]
+    n = len(xs)
+    x, y = F.from_ints(xs), F.from_ints(ys)
+    r, h = F.alloc(n), F.alloc(n)
+    assert F.to_ints(x) == xs
+    F.modpro(x, h)
+    assert F.to_ints(h) == [O.modpro(v) for v in xs]
+    F.modinv(x, h, r)
+    assert F.to_ints(r) == [O.modinv(v) for v in xs]
+    F.modsqrt(x, h, r)
+    assert F.to_ints(r) == [O.modsqrt(v) for v in xs]
+    assert F.modqr(h, x).cpu().tolist() == [O.modqr(None, v) for v in xs]
+    assert F.modis1(x).cpu().tolist() == [int(v == 1) for v in xs]
+    assert F.modis0(x).cpu().tolist() == [int(v == 0) for v in xs]
+    F.modcpy(x, r); F.modnsqr(r, 7)
+    assert F.to_ints(r) == [pow(v, 128, p) for v in xs]
+    F.modone(r); assert F.to_ints(r) == [1] * n
+    F.modzer(r); assert F.to_ints(r) == [0] * n
+    F.modint(12345, r); assert F.to_ints(r) == [12345] * n
+    # nres / redc: plain side is the canonical value as little-endian 32-bit word planes
+    plain = F.alloc(n)
+    F.redc(x, plain)
+    pw = plain.cpu().numpy().astype(np.uint32)
+    assert [sum(int(pw[j, i]) << (32 * j) for j in range(F.Nlimbs)) for i in range(n)] == xs
+    F.nres(plain, r)
+    assert F.to_ints(r) == xs
+    bits = torch.tensor([i & 1 for i in range(n)], dtype=torch.int32, device="cuda")
+    g_, f_ = x.clone(), y.clone()
+    F.modcsw(bits, g_, f_)
+    assert F.to_ints(g_) == [ys[i] if i & 1 else xs[i] for i in range(n)]
+    assert F.to_ints(f_) == [xs[i] if i & 1 else ys[i] for i in range(n)]
+    f_ = y.clone()
+    F.modcmv(bits, x, f_)
+    assert F.to_ints(f_) == [xs[i] if i & 1 else ys[i] for i in range(n)]
+    F.modcpy(x, r); F.modshl(5, r)
+    assert F.to_ints(r) == [O.modshl(5, v) for v in xs]
+    F.modcpy(x, r); F.modhaf(r)
+    assert F.to_ints(r) == [O.modhaf(v) for v in xs]
+    assert F.modsign(x).cpu().tolist() == [v & 1 for v in xs]
+    assert F.modcmp(x, y).cpu().tolist() == [int(a == b) for a, b in zip(xs, ys)]
+    assert F.modcmp(x, x).cpu().tolist() == [1] * n
+    F.modcpy(x, r)
+    assert F.modfsb(r).cpu().tolist() == [1] * n
+    for rr in (0, 31, 32, 200, O.P.nbits - 1, 8 * O.nbytes - 1, 8 * O.nbytes):
+        F.mod2r(rr, r)
+        assert F.to_ints(r)[:3] == [O.mod2r(rr)] * 3
+    if name != "NIST256":          # modshr acts on the stored value (plain for these moduli)
+        F.modcpy(x, r)
+        out = F.modshr(8, r).cpu().tolist()
+        assert list(zip(F.to_ints(r), out)) == [O.modshr(8, v) for v in xs]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_aliasing_and_pitch(name):
+    """Outputs may alias inputs (pseudo.py:1832-1845); planes may be a window of a wider pitch."""
+    F = _field(name)
+    O = FieldOracle(name)
+    p = O.p
+    rng = random.Random(3)
+    n = 100
+    xs, ys = [rng.randrange(p) for _ in range(n)], [rng.randrange(p) for _ in range(n)]
+    x, y = F.from_ints(xs), F.from_ints(ys)
+    F.modmul(x, y, x)
+    assert F.to_ints(x) == [a * b % p for a, b in zip(xs, ys)]
+    F.modadd(y, y, y)
+    assert F.to_ints(y) == [2 * b % p for b in ys]
+    F.modinv(y, None, y)
+    assert F.to_ints(y) == [pow(2 * b, -1, p) for b in ys]
+    wide = torch.zeros((F.Nlimbs, 4 * n), dtype=torch.int32, device="cuda")
+    a, b, c = wide[:, 0:n], wide[:, n:2 * n], wide[:, 3 * n:4 * n]
+    a.copy_(F.from_ints(xs)); b.copy_(F.from_ints(ys))
+    F.modmul(a, b, c)
+    assert F.to_ints(c.contiguous()) == [u * v % p for u, v in zip(xs, ys)]
+    assert int(wide[:, 2 * n:3 * n].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_selftest_sequence(name):
+    """The generator's own ctypes self-test (pseudo.py:1762-1855), 1000 random x,y, run through the
+    batched ABI: redc(...) must equal ((x-y)(x+y))^-2.  (modshl/modshr pair omitted: DESIGN.md.)"""
+    F = _field(name)
+    p = PRIMES[name].p
+    rng = random.Random(4)
+    lim = min(2 * p, 1 << (8 * F.Nbytes))
+    xs, ys = [rng.randrange(lim) for _ in range(1000)], [rng.randrange(lim) for _ in range(1000)]
+    x, y = F.from_ints(xs), F.from_ints(ys)
+    t, z = F.alloc(1000), F.alloc(1000)
+    F.modadd(x, y, t)
+    F.modsub(x, y, z)
+    F.modmul(t, z, x)
+    F.modsqr(x, z)
+    F.modinv(z, None, z)
+    F.modsqrt(z, None, z)
+    F.modsqr(z, z)
+    F.modhaf(z)
+    F.modadd(z, z, z)
+    got = F.to_ints(z)
+    for i in range(1000):
+        w = (xs[i] - ys[i]) * (xs[i] + ys[i]) % p
+        assert got[i] == (pow(w * w % p, -1, p) if w else 0)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_large_batch_vs_reference_build(ref_libs, name):
+    key = name if name == "NIST256" else name + "_generic"
+    if key not in ref_libs:
+        pytest.skip("oracle/_ref not built")
+    F = _field(name)
+    nb = F.Nbytes
+    n = 1 << 15
+    a, b = util.random_bytes(41, n, nb), util.random_bytes(42, n, nb)
+    # explicit corner rows: p-1, p, p+1, 2^(8*Nbytes)-1, 0, 1
+    p = PRIMES[name].p
+    for i, v in enumerate([p - 1, p, p + 1, (1 << (8 * nb)) - 1, 0, 1]):
+        a[i] = np.frombuffer(v.to_bytes(nb, "big"), dtype=np.uint8)
+    x, st = F.modimp(torch.from_numpy(a).cuda())
+    y, _ = F.modimp(torch.from_numpy(b).cuda())
+    r = F.alloc(n)
+    for op in ("mul", "sqr", "inv", "sqrt", "add", "sub"):
+        want, wst = util.ref_field_batch(ref_libs[key], op, a, b if op in ("mul", "add", "sub") else None)
+        if op == "mul": F.modmul(x, y, r)
+        if op == "sqr": F.modsqr(x, r)
+        if op == "inv": F.modinv(x, None, r)
+        if op == "sqrt": F.modsqrt(x, None, r)
+        if op == "add": F.modadd(x, y, r)
+        if op == "sub": F.modsub(x, y, r)
+        assert np.array_equal(_bytes(F.modexp(r)), want), (name, op)
+        assert np.array_equal(st.cpu().numpy(), wst)
+
+
+def test_p256_full_size_properties():
+    """BASELINE config 4 (2^24 P-256 elements): size-independent identities on the whole batch:
+    a * a^-1 == 1 (a != 0), sqrt(a^2)^2 == a^2, (a+b)-b == a, a*b == b*a."""
+    F = _field("NIST256")
+    n = 1 << 24
+    gen = torch.Generator(device="cuda").manual_seed(256)
+    a8 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=gen)
+    b8 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=gen)
+    x, _ = F.modimp(a8)
+    y, _ = F.modimp(b8)
+    del a8, b8
+    r, s = F.alloc(n), F.alloc(n)
+    F.modinv(x, None, r)
+    F.modmul(r, x, r)
+    assert int(F.modis1(r).sum()) + int(F.modis0(x).sum()) == n
+    F.modsqr(x, r)
+    F.modsqrt(r, None, s)
+    F.modsqr(s, s)
+    assert int(F.modcmp(r, s).sum()) == n
+    F.modadd(x, y, r)
+    F.modsub(r, y, r)
+    assert int(F.modcmp(r, x).sum()) == n
+    F.modmul(x, y, r)
+    F.modmul(y, x, s)
+    assert int(F.modcmp(r, s).sum()) == n
