@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="keys in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the X448 / P-256 side measurements")
     return ap.parse_args()
 
 
@@ -162,6 +163,74 @@ def imad_peak(lib, sms):
     return res
 
 
+def _time(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def extra_measurements(lib, mlib, dev, peak, hbm_peak):
+    """Side figures for the other BASELINE configs (rank 0, one GPU): X448 ladder, P-256 field ops.
+    Single field operations per launch are HBM-bound (96 B per 64 products) and reported against the
+    measured copy bandwidth; register-resident chains are reported against the IMAD peak."""
+    import torch
+    from modarith_b200 import Field
+    from modarith_b200.rfc7748 import rfc7748
+    pk = peak["peak_products_per_s"] if peak else None
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(448)
+    n = 1 << 20
+    k = torch.randint(0, 256, (n, 56), dtype=torch.uint8, device=dev, generator=gen)
+    u = torch.randint(0, 256, (n, 56), dtype=torch.uint8, device=dev, generator=gen)
+    v = torch.empty_like(k)
+    t = _time(lambda: rfc7748("X448", k, u, v), 3)
+    prod = mlib.products("X448", "rfc7748")
+    out["x448"] = {"workload": "X448 ladder, 2^20 keys", "value": n / t, "unit": "scalar-mults/s",
+                   "products_per_key": prod, "imad_frac": (n / t * prod / pk) if pk else None}
+    del k, u, v
+    for name, nel in (("NIST256", 1 << 24), ("X25519", 1 << 22)):
+        F = Field(name, dev)
+        a8 = torch.randint(0, 256, (nel, F.Nbytes), dtype=torch.uint8, device=dev, generator=gen)
+        b8 = torch.randint(0, 256, (nel, F.Nbytes), dtype=torch.uint8, device=dev, generator=gen)
+        x, _ = F.modimp(a8)
+        y, _ = F.modimp(b8)
+        del a8, b8
+        r = F.alloc(nel)
+        L = F.Nlimbs
+        res = {"elements": nel}
+        t = _time(lambda: F.modmul(x, y, r), 5)
+        res["modmul_single_launch"] = {"value": nel / t / 1e9, "unit": "Gop/s", "hbm_GBps": nel * 12 * L / t / 1e9,
+                                       "hbm_frac": nel * 12 * L / t / 1e9 / hbm_peak,
+                                       "imad_frac": (nel / t * L * L / pk) if pk else None}
+        t = _time(lambda: F.modadd(x, y, r), 5)
+        res["modadd_single_launch"] = {"value": nel / t / 1e9, "unit": "Gop/s", "hbm_GBps": nel * 12 * L / t / 1e9,
+                                       "hbm_frac": nel * 12 * L / t / 1e9 / hbm_peak}
+        m, iters = 1 << 21, 512
+        xs, ys, rs = x[:, :m].contiguous(), y[:, :m].contiguous(), r[:, :m].contiguous()
+        t = _time(lambda: F.bench_modmul(xs, ys, rs, iters), 2)
+        res["modmul_register_resident"] = {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
+                                           "imad_frac": (m * iters / t * L * L / pk) if pk else None}
+        t = _time(lambda: F.modnsqr(rs, iters), 2)
+        res["modsqr_register_resident"] = {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
+                                           "imad_frac": (m * iters / t * (L * (L + 1) // 2) / pk) if pk else None}
+        t = _time(lambda: F.modinv(xs, None, rs), 2)
+        pi = mlib.products(name, "modinv")
+        res["modinv"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": pi, "imad_frac": (m / t * pi / pk) if pk else None}
+        t = _time(lambda: F.modsqrt(xs, None, rs), 2)
+        ps = mlib.products(name, "modsqrt")
+        res["modsqrt"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": ps, "imad_frac": (m / t * ps / pk) if pk else None}
+        out[name] = res
+        del x, y, r, xs, ys, rs
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args, rank):
     if rank != 0:
@@ -191,7 +260,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "X25519 scalar-mults/s", "value": v, "unit": "scalar-mults/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (radix 2^51) on CPU",
-        "data": "synthetic", "config": {"workload": "batched X25519 (rfc7748) random scalars/points, CPU sample of %d keys per step" % n},
+        "data": "synthetic",
+        "config": {"workload": "batched X25519 (rfc7748) 2^20 random scalars/points per GPU", "keys_per_gpu": args.keys,
+                   "cpu_sample_keys_per_step": n, "inputs": "numpy PCG64(7748) raw bytes, unclamped / unreduced"},
         "cpu_baseline": {"value": v, "unit": "scalar-mults/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "scalar-mults/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -276,11 +347,15 @@ def main():
         rfc7748(CURVE, hk[w % NSETS], hu[w % NSETS], hv, device=local)
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for s in range(args.steps):
+        ts = time.perf_counter()
         rfc7748(CURVE, hk[s % NSETS], hu[s % NSETS], hv, device=local)
+        e2e_steps.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    chunks = (n_local + (1 << 17) - 1) >> 17
+    per_chunk = 2 * props.multi_processor_count * 4 * 128          # mab_capi.inc: two waves of resident CTAs
+    chunks = (n_local + per_chunk - 1) // per_chunk
     e2e_launches = args.steps * chunks
     if ref is not None and parity:
         _, want = time_reference(ref, hk[(args.steps - 1) % NSETS][:1024].numpy(), hu[(args.steps - 1) % NSETS][:1024].numpy(), 0)
@@ -336,6 +411,7 @@ def main():
                 roof["traffic"] = json.load(open(tr)).get("k_rfc7748_X25519_dram_bytes_per_launch")
             except Exception:
                 pass
+        extra = None if args.no_extra else extra_measurements(lib, mlib, dev, peak, hbm_peak)
         base = None if args.no_cpu_baseline else cpu_baseline(args.cpu_sample)
         line = {
             "metric": "X25519 scalar-mults/s", "value": value, "unit": "scalar-mults/s", "n_gpus": world,
@@ -349,10 +425,13 @@ def main():
                        "inputs": "numpy PCG64(7748+...) raw bytes, unclamped / unreduced"},
             "e2e": {"value": e2e, "unit": "scalar-mults/s", "h2d_bytes_per_step": 2 * NB * n_local,
                     "d2h_bytes_per_step": NB * n_local, "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step_min_median_max_rank0": [1e3 * min(e2e_steps), 1e3 * statistics.median(e2e_steps),
+                                                         1e3 * max(e2e_steps)],
                     "api": "mab_X25519_rfc7748_host (pinned host buffers, 3-stream chunked pipeline)"},
             "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
             "roofline": roof, "cpu_baseline": base, "clocks": clocks, "parity_spot_check": parity,
             "gather_ms": gather_ms_max if world > 1 else None, "gpu": props.name, "sms": props.multi_processor_count,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:

@@ -51,6 +51,9 @@ extern "C" {
 MAB_API const char *mab_version(void);
 MAB_API const char *mab_error_string(int code);
 MAB_API int mab_device_count(void);
+/* The *_host entry points keep three streams and staging buffers per device between calls;
+ * this frees them (optional; they are also reclaimed at process exit). */
+MAB_API void mab_release_workspaces(void);
 /* Parameters of a modulus by name ("X25519", ...): Wordlength/Nlimbs/Radix/Nbits/Nbytes macros
  * of the generated header (pseudo.py:1403-1407).  Returns 0, or MAB_ERR_BADARG. */
 MAB_API int mab_params(const char *prime, int *wordlength, int *nlimbs, int *radix, int *nbits, int *nbytes);
@@ -64,6 +67,11 @@ MAB_API long long mab_products(const char *prime, const char *what);
  * Writes elapsed milliseconds and the number of multiply instructions executed by all threads. */
 MAB_API int mab_imad_peak(int variant, int iters, int blocks, int threads, float *ms, double *instructions, void *stream);
 
+/* Instruction-mix probe (generated, csrc/mab_probe.cuh): times one PTX block mixing IMAD.WIDE and
+ * ALU-pipe instructions; returns the mix through name/nwide/nalu.  Variants 0..13; see tools/run_probe.py. */
+MAB_API int mab_pipe_probe(int variant, int iters, int blocks, int threads, float *ms, const char **name,
+                           int *nwide, int *nalu, void *stream);
+
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
   /* modfsb   pseudo.py:272-283   canonicalise in place; was_lt[i]=1 iff stored value was < p (may be NULL) */ \
@@ -76,6 +84,8 @@ MAB_API int mab_imad_peak(int variant, int iters, int blocks, int threads, float
   MAB_API int mab_##P##_modneg(const uint32_t *b, uint32_t *n_, size_t n, size_t stride, void *stream);           \
   /* modmul   pseudo.py:616-659, monty.py:663-872 */                                                      \
   MAB_API int mab_##P##_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, size_t n, size_t stride, void *stream); \
+  /* measurement helper, not part of the reference API: c = a * b^iters, product kept in registers */  \
+  MAB_API int mab_##P##_bench_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, unsigned int iters, size_t n, size_t stride, void *stream); \
   /* modsqr   pseudo.py:663-702, monty.py:982-1165 */                                                     \
   MAB_API int mab_##P##_modsqr(const uint32_t *a, uint32_t *c, size_t n, size_t stride, void *stream);            \
   /* modmli   pseudo.py:705-728, monty.py:876-978   0 <= b < 2^31 */                                      \

@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmodarith_b200.so")
 OBJDIR = os.path.join(PKG, "build")
 
-NVCC_FLAGS = ["-I", CSRC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-I", CSRC, "-I", os.path.join(PKG, "..", "include"), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = ["mab_capi_X25519.cu", "mab_capi_X448.cu", "mab_capi_NIST256.cu", "mab_runtime.cu"]
 

@@ -2,9 +2,10 @@
 // Command line : python -m modarith_b200.gen.monty_sm100 NIST256
 // modulus NIST256 = 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff
 // plan Montgomery: 8 saturated 32-bit limbs; stored values < p; R = 2^256
-//   mul   :  64 IMAD.WIDE   0 IMAD  ~122 ALU-pipe ops
-//   sqr   :  36 IMAD.WIDE   0 IMAD  ~134 ALU-pipe ops
+//   mul   :  64 IMAD.WIDE   0 IMAD  ~116 ALU-pipe ops
+//   sqr   :  36 IMAD.WIDE   0 IMAD  ~128 ALU-pipe ops
 //   mli   :   8 IMAD.WIDE   0 IMAD  ~102 ALU-pipe ops
+//   mla   :   8 IMAD.WIDE   0 IMAD  ~103 ALU-pipe ops
 //   add   :   0 IMAD.WIDE   0 IMAD  ~ 43 ALU-pipe ops
 //   sub   :   0 IMAD.WIDE   0 IMAD  ~ 18 ALU-pipe ops
 //   canon :   0 IMAD.WIDE   0 IMAD  ~ 34 ALU-pipe ops
@@ -19,6 +20,7 @@ struct F_NIST256 {
   static constexpr int PM1D2 = 1;
   static constexpr bool MONTGOMERY = true;
   static constexpr int PRO_SQR = 253, PRO_MUL = 12;
+  static constexpr int LADDER_MINBLOCKS = 4;   // resident 128-thread CTAs per SM for k_rfc7748
   static constexpr bool HAS_CURVE = false;
   static constexpr uint32_t A24 = 0;
   static constexpr int COF = 0;
@@ -53,8 +55,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t6, %13, %17, t6;\n\t"
         "madc.hi.cc.u32 t7, %13, %17, t7;\n\t"
         "madc.lo.cc.u32 t8, %15, %17, 0x0;\n\t"
-        "madc.hi.cc.u32 t9, %15, %17, 0x0;\n\t"
-        "addc.u32 t10, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t9, %15, %17, 0x0;\n\t"
         "mad.lo.cc.u32 t17, %8, %17, t17;\n\t"
         "madc.hi.cc.u32 t18, %8, %17, t18;\n\t"
         "madc.lo.cc.u32 t19, %10, %17, t19;\n\t"
@@ -72,7 +73,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t7, %12, %18, t7;\n\t"
         "madc.lo.cc.u32 t8, %14, %18, t8;\n\t"
         "madc.hi.cc.u32 t9, %14, %18, t9;\n\t"
-        "addc.u32 t10, t10, 0x0;\n\t"
+        "addc.u32 t10, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t19, %9, %18, t19;\n\t"
         "madc.hi.cc.u32 t20, %9, %18, t20;\n\t"
         "madc.lo.cc.u32 t21, %11, %18, t21;\n\t"
@@ -80,8 +81,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t23, %13, %18, t23;\n\t"
         "madc.hi.cc.u32 t24, %13, %18, t24;\n\t"
         "madc.lo.cc.u32 t25, %15, %18, t25;\n\t"
-        "madc.hi.cc.u32 t26, %15, %18, 0x0;\n\t"
-        "addc.u32 t27, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t26, %15, %18, 0x0;\n\t"
         "mad.lo.cc.u32 t4, %9, %19, t4;\n\t"
         "madc.hi.cc.u32 t5, %9, %19, t5;\n\t"
         "madc.lo.cc.u32 t6, %11, %19, t6;\n\t"
@@ -89,8 +89,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t8, %13, %19, t8;\n\t"
         "madc.hi.cc.u32 t9, %13, %19, t9;\n\t"
         "madc.lo.cc.u32 t10, %15, %19, t10;\n\t"
-        "madc.hi.cc.u32 t11, %15, %19, 0x0;\n\t"
-        "addc.u32 t12, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t11, %15, %19, 0x0;\n\t"
         "mad.lo.cc.u32 t19, %8, %19, t19;\n\t"
         "madc.hi.cc.u32 t20, %8, %19, t20;\n\t"
         "madc.lo.cc.u32 t21, %10, %19, t21;\n\t"
@@ -99,7 +98,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t24, %12, %19, t24;\n\t"
         "madc.lo.cc.u32 t25, %14, %19, t25;\n\t"
         "madc.hi.cc.u32 t26, %14, %19, t26;\n\t"
-        "addc.u32 t27, t27, 0x0;\n\t"
+        "addc.u32 t27, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t4, %8, %20, t4;\n\t"
         "madc.hi.cc.u32 t5, %8, %20, t5;\n\t"
         "madc.lo.cc.u32 t6, %10, %20, t6;\n\t"
@@ -108,7 +107,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t9, %12, %20, t9;\n\t"
         "madc.lo.cc.u32 t10, %14, %20, t10;\n\t"
         "madc.hi.cc.u32 t11, %14, %20, t11;\n\t"
-        "addc.u32 t12, t12, 0x0;\n\t"
+        "addc.u32 t12, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t21, %9, %20, t21;\n\t"
         "madc.hi.cc.u32 t22, %9, %20, t22;\n\t"
         "madc.lo.cc.u32 t23, %11, %20, t23;\n\t"
@@ -116,8 +115,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t25, %13, %20, t25;\n\t"
         "madc.hi.cc.u32 t26, %13, %20, t26;\n\t"
         "madc.lo.cc.u32 t27, %15, %20, t27;\n\t"
-        "madc.hi.cc.u32 t28, %15, %20, 0x0;\n\t"
-        "addc.u32 t29, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t28, %15, %20, 0x0;\n\t"
         "mad.lo.cc.u32 t6, %9, %21, t6;\n\t"
         "madc.hi.cc.u32 t7, %9, %21, t7;\n\t"
         "madc.lo.cc.u32 t8, %11, %21, t8;\n\t"
@@ -125,8 +123,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t10, %13, %21, t10;\n\t"
         "madc.hi.cc.u32 t11, %13, %21, t11;\n\t"
         "madc.lo.cc.u32 t12, %15, %21, t12;\n\t"
-        "madc.hi.cc.u32 t13, %15, %21, 0x0;\n\t"
-        "addc.u32 t14, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t13, %15, %21, 0x0;\n\t"
         "mad.lo.cc.u32 t21, %8, %21, t21;\n\t"
         "madc.hi.cc.u32 t22, %8, %21, t22;\n\t"
         "madc.lo.cc.u32 t23, %10, %21, t23;\n\t"
@@ -135,7 +132,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t26, %12, %21, t26;\n\t"
         "madc.lo.cc.u32 t27, %14, %21, t27;\n\t"
         "madc.hi.cc.u32 t28, %14, %21, t28;\n\t"
-        "addc.u32 t29, t29, 0x0;\n\t"
+        "addc.u32 t29, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t6, %8, %22, t6;\n\t"
         "madc.hi.cc.u32 t7, %8, %22, t7;\n\t"
         "madc.lo.cc.u32 t8, %10, %22, t8;\n\t"
@@ -144,7 +141,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t11, %12, %22, t11;\n\t"
         "madc.lo.cc.u32 t12, %14, %22, t12;\n\t"
         "madc.hi.cc.u32 t13, %14, %22, t13;\n\t"
-        "addc.u32 t14, t14, 0x0;\n\t"
+        "addc.u32 t14, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t23, %9, %22, t23;\n\t"
         "madc.hi.cc.u32 t24, %9, %22, t24;\n\t"
         "madc.lo.cc.u32 t25, %11, %22, t25;\n\t"
@@ -152,8 +149,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t27, %13, %22, t27;\n\t"
         "madc.hi.cc.u32 t28, %13, %22, t28;\n\t"
         "madc.lo.cc.u32 t29, %15, %22, t29;\n\t"
-        "madc.hi.cc.u32 t30, %15, %22, 0x0;\n\t"
-        "addc.u32 t31, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t30, %15, %22, 0x0;\n\t"
         "mad.lo.cc.u32 t8, %9, %23, t8;\n\t"
         "madc.hi.cc.u32 t9, %9, %23, t9;\n\t"
         "madc.lo.cc.u32 t10, %11, %23, t10;\n\t"
@@ -170,7 +166,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t28, %12, %23, t28;\n\t"
         "madc.lo.cc.u32 t29, %14, %23, t29;\n\t"
         "madc.hi.cc.u32 t30, %14, %23, t30;\n\t"
-        "addc.u32 t31, t31, 0x0;\n\t"
+        "addc.u32 t31, 0x0, 0x0;\n\t"
         "add.cc.u32 t32, t1, t17;\n\t"
         "addc.cc.u32 t33, t2, t18;\n\t"
         "addc.cc.u32 t34, t3, t19;\n\t"
@@ -333,8 +329,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_1_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_1_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_1_i) + 0x0u + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_1_i) >> 32) + 0x0u + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t10 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_1_i) >> 32) + 0x0u + cf_; t9 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_1_i) + t17; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_1_i) >> 32) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_1_i) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -352,7 +347,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_2_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_2_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_2_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t10 + 0x0u + cf_; t10 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t10 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_2_i) + t19; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_2_i) >> 32) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_2_i) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -360,8 +355,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_2_i) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_2_i) >> 32) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_2_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_2_i) >> 32) + 0x0u + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t27 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_2_i) >> 32) + 0x0u + cf_; t26 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_3_i) + t4; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_3_i) >> 32) + t5 + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_3_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -369,8 +363,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_3_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_3_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_3_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_3_i) >> 32) + 0x0u + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t12 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_3_i) >> 32) + 0x0u + cf_; t11 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_3_i) + t19; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_3_i) >> 32) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_3_i) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -379,7 +372,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_3_i) >> 32) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_3_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_3_i) >> 32) + t26 + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t27 + 0x0u + cf_; t27 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t27 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_4_i) + t4; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_4_i) >> 32) + t5 + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_4_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -388,7 +381,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_4_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_4_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_4_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t12 + 0x0u + cf_; t12 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t12 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_4_i) + t21; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_4_i) >> 32) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_4_i) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -396,8 +389,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_4_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_4_i) >> 32) + t26 + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_4_i) + t27 + cf_; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_4_i) >> 32) + 0x0u + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t29 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_4_i) >> 32) + 0x0u + cf_; t28 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_5_i) + t6; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_5_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_5_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -405,8 +397,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_5_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_5_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_5_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_5_i) >> 32) + 0x0u + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t14 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_5_i) >> 32) + 0x0u + cf_; t13 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_5_i) + t21; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_5_i) >> 32) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_5_i) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -415,7 +406,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_5_i) >> 32) + t26 + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_5_i) + t27 + cf_; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_5_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t29 + 0x0u + cf_; t29 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t29 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_6_i) + t6; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_6_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_6_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -424,7 +415,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_6_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_6_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_6_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t14 + 0x0u + cf_; t14 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t14 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_6_i) + t23; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_6_i) >> 32) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_6_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -432,8 +423,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_5_i * b_6_i) + t27 + cf_; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * b_6_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * b_6_i) + t29 + cf_; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * b_6_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t31 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * b_6_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_7_i) + t8; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_7_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_7_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -450,7 +440,7 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_4_i * b_7_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_7_i) + t29 + cf_; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_7_i) >> 32) + t30 + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t31 + 0x0u + cf_; t31 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t31 = (uint32_t)w_;
     w_ = (uint64_t)t1 + t17; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t2 + t18 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t19 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -595,8 +585,7 @@ struct F_NIST256 {
         "madc.lo.cc.u32 t6, %9, %13, t6;\n\t"
         "madc.hi.cc.u32 t7, %9, %13, t7;\n\t"
         "madc.lo.cc.u32 t8, %9, %15, 0x0;\n\t"
-        "madc.hi.cc.u32 t9, %9, %15, 0x0;\n\t"
-        "addc.u32 t10, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t9, %9, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t19, %9, %10, t19;\n\t"
         "madc.hi.cc.u32 t20, %9, %10, t20;\n\t"
         "madc.lo.cc.u32 t21, %9, %12, t21;\n\t"
@@ -608,41 +597,36 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t7, %10, %12, t7;\n\t"
         "madc.lo.cc.u32 t8, %10, %14, t8;\n\t"
         "madc.hi.cc.u32 t9, %10, %14, t9;\n\t"
-        "addc.u32 t10, t10, 0x0;\n\t"
+        "addc.u32 t10, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t21, %10, %11, t21;\n\t"
         "madc.hi.cc.u32 t22, %10, %11, t22;\n\t"
         "madc.lo.cc.u32 t23, %10, %13, t23;\n\t"
         "madc.hi.cc.u32 t24, %10, %13, t24;\n\t"
         "madc.lo.cc.u32 t25, %10, %15, t25;\n\t"
-        "madc.hi.cc.u32 t26, %10, %15, 0x0;\n\t"
-        "addc.u32 t27, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t26, %10, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t8, %11, %13, t8;\n\t"
         "madc.hi.cc.u32 t9, %11, %13, t9;\n\t"
         "madc.lo.cc.u32 t10, %11, %15, t10;\n\t"
-        "madc.hi.cc.u32 t11, %11, %15, 0x0;\n\t"
-        "addc.u32 t12, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t11, %11, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t23, %11, %12, t23;\n\t"
         "madc.hi.cc.u32 t24, %11, %12, t24;\n\t"
         "madc.lo.cc.u32 t25, %11, %14, t25;\n\t"
         "madc.hi.cc.u32 t26, %11, %14, t26;\n\t"
-        "addc.u32 t27, t27, 0x0;\n\t"
+        "addc.u32 t27, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t10, %12, %14, t10;\n\t"
         "madc.hi.cc.u32 t11, %12, %14, t11;\n\t"
-        "addc.u32 t12, t12, 0x0;\n\t"
+        "addc.u32 t12, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t25, %12, %13, t25;\n\t"
         "madc.hi.cc.u32 t26, %12, %13, t26;\n\t"
         "madc.lo.cc.u32 t27, %12, %15, t27;\n\t"
-        "madc.hi.cc.u32 t28, %12, %15, 0x0;\n\t"
-        "addc.u32 t29, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t28, %12, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t12, %13, %15, t12;\n\t"
-        "madc.hi.cc.u32 t13, %13, %15, 0x0;\n\t"
-        "addc.u32 t14, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t13, %13, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t27, %13, %14, t27;\n\t"
         "madc.hi.cc.u32 t28, %13, %14, t28;\n\t"
-        "addc.u32 t29, t29, 0x0;\n\t"
+        "addc.u32 t29, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t29, %14, %15, t29;\n\t"
-        "madc.hi.cc.u32 t30, %14, %15, 0x0;\n\t"
-        "addc.u32 t31, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t30, %14, %15, 0x0;\n\t"
         "add.cc.u32 t32, t2, t18;\n\t"
         "addc.cc.u32 t33, t3, t19;\n\t"
         "addc.cc.u32 t34, t4, t20;\n\t"
@@ -655,8 +639,8 @@ struct F_NIST256 {
         "addc.cc.u32 t41, t11, t27;\n\t"
         "addc.cc.u32 t42, t12, t28;\n\t"
         "addc.cc.u32 t43, t13, t29;\n\t"
-        "addc.cc.u32 t44, t14, t30;\n\t"
-        "addc.u32 t45, 0x0, t31;\n\t"
+        "addc.cc.u32 t44, 0x0, t30;\n\t"
+        "addc.u32 t45, 0x0, 0x0;\n\t"
         "shl.b32 t46, t17, 1;\n\t"
         "shf.l.wrap.b32 t47, t17, t32, 1;\n\t"
         "shf.l.wrap.b32 t48, t32, t33, 1;\n\t"
@@ -823,8 +807,7 @@ struct F_NIST256 {
     w_ = (uint64_t)(uint32_t)(a_1_i * a_5_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * a_5_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_1_i * a_7_i) + 0x0u + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_1_i * a_7_i) >> 32) + 0x0u + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t10 = (uint32_t)w_;
+    w_ = (((uint64_t)a_1_i * a_7_i) >> 32) + 0x0u + cf_; t9 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * a_2_i) + t19; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * a_2_i) >> 32) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_1_i * a_4_i) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -836,41 +819,36 @@ struct F_NIST256 {
     w_ = (((uint64_t)a_2_i * a_4_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_6_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_6_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t10 + 0x0u + cf_; t10 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t10 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_2_i * a_3_i) + t21; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_3_i) >> 32) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_5_i) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_5_i) >> 32) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_7_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_2_i * a_7_i) >> 32) + 0x0u + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t27 = (uint32_t)w_;
+    w_ = (((uint64_t)a_2_i * a_7_i) >> 32) + 0x0u + cf_; t26 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_3_i * a_5_i) + t8; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_5_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_7_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_3_i * a_7_i) >> 32) + 0x0u + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t12 = (uint32_t)w_;
+    w_ = (((uint64_t)a_3_i * a_7_i) >> 32) + 0x0u + cf_; t11 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_3_i * a_4_i) + t23; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_4_i) >> 32) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_6_i) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_6_i) >> 32) + t26 + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t27 + 0x0u + cf_; t27 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t27 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_4_i * a_6_i) + t10; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_6_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t12 + 0x0u + cf_; t12 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t12 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_4_i * a_5_i) + t25; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_5_i) >> 32) + t26 + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_4_i * a_7_i) + t27 + cf_; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_4_i * a_7_i) >> 32) + 0x0u + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t29 = (uint32_t)w_;
+    w_ = (((uint64_t)a_4_i * a_7_i) >> 32) + 0x0u + cf_; t28 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_5_i * a_7_i) + t12; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_5_i * a_7_i) >> 32) + 0x0u + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t14 = (uint32_t)w_;
+    w_ = (((uint64_t)a_5_i * a_7_i) >> 32) + 0x0u + cf_; t13 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_5_i * a_6_i) + t27; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * a_6_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t29 + 0x0u + cf_; t29 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t29 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_6_i * a_7_i) + t29; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_6_i * a_7_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t31 = (uint32_t)w_;
+    w_ = (((uint64_t)a_6_i * a_7_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_;
     w_ = (uint64_t)t2 + t18; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t19 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t4 + t20 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -883,8 +861,8 @@ struct F_NIST256 {
     w_ = (uint64_t)t11 + t27 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t12 + t28 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t13 + t29 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t14 + t30 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + t31 + cf_; t45 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + t30 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t45 = (uint32_t)w_;
     t46 = (uint32_t)(t17 << 1);
     t47 = (uint32_t)(((((uint64_t)t32 << 32) | t17) << 1) >> 32);
     t48 = (uint32_t)(((((uint64_t)t33 << 32) | t32) << 1) >> 32);
@@ -1293,6 +1271,291 @@ struct F_NIST256 {
     r[5] = t111;
     r[6] = t114;
     r[7] = t117;
+#endif
+  }
+
+  // r = a*b + c, small integer b: modmli + modadd fused (rfc7748.c:209,212)
+  static MAB_DEV void mla(uint32_t (&r)[8], const uint32_t (&a)[8], uint32_t b, const uint32_t (&c)[8]) {
+#ifndef MAB_HOSTSIM
+    asm("{\n\t"
+        ".reg .u32 t<119>;\n\t"
+        "mad.lo.cc.u32 t0, %8, %24, %16;\n\t"
+        "madc.hi.cc.u32 t1, %8, %24, %17;\n\t"
+        "madc.lo.cc.u32 t2, %10, %24, %18;\n\t"
+        "madc.hi.cc.u32 t3, %10, %24, %19;\n\t"
+        "madc.lo.cc.u32 t4, %12, %24, %20;\n\t"
+        "madc.hi.cc.u32 t5, %12, %24, %21;\n\t"
+        "madc.lo.cc.u32 t6, %14, %24, %22;\n\t"
+        "madc.hi.cc.u32 t7, %14, %24, %23;\n\t"
+        "addc.u32 t8, 0x0, 0x0;\n\t"
+        "mul.lo.u32 t9, %9, %24;\n\t"
+        "mul.hi.u32 t10, %9, %24;\n\t"
+        "mul.lo.u32 t11, %11, %24;\n\t"
+        "mul.hi.u32 t12, %11, %24;\n\t"
+        "mul.lo.u32 t13, %13, %24;\n\t"
+        "mul.hi.u32 t14, %13, %24;\n\t"
+        "mul.lo.u32 t15, %15, %24;\n\t"
+        "mul.hi.u32 t16, %15, %24;\n\t"
+        "add.cc.u32 t17, t1, t9;\n\t"
+        "addc.cc.u32 t18, t2, t10;\n\t"
+        "addc.cc.u32 t19, t3, t11;\n\t"
+        "addc.cc.u32 t20, t4, t12;\n\t"
+        "addc.cc.u32 t21, t5, t13;\n\t"
+        "addc.cc.u32 t22, t6, t14;\n\t"
+        "addc.cc.u32 t23, t7, t15;\n\t"
+        "addc.u32 t24, t8, t16;\n\t"
+        "add.cc.u32 t25, t0, t24;\n\t"
+        "addc.cc.u32 t26, t17, 0x0;\n\t"
+        "addc.cc.u32 t27, t18, 0x0;\n\t"
+        "addc.cc.u32 t28, t19, 0x0;\n\t"
+        "addc.cc.u32 t29, t20, 0x0;\n\t"
+        "addc.cc.u32 t30, t21, 0x0;\n\t"
+        "addc.cc.u32 t31, t22, 0x0;\n\t"
+        "addc.cc.u32 t32, t23, 0x0;\n\t"
+        "addc.u32 t33, 0x0, 0x0;\n\t"
+        "add.cc.u32 t34, t32, t24;\n\t"
+        "addc.u32 t35, t33, 0x0;\n\t"
+        "sub.cc.u32 t36, t28, t24;\n\t"
+        "subc.cc.u32 t37, t29, 0x0;\n\t"
+        "subc.cc.u32 t38, t30, 0x0;\n\t"
+        "subc.cc.u32 t39, t31, 0x0;\n\t"
+        "subc.cc.u32 t40, t34, 0x0;\n\t"
+        "subc.u32 t41, t35, 0x0;\n\t"
+        "sub.cc.u32 t42, t39, t24;\n\t"
+        "subc.cc.u32 t43, t40, 0x0;\n\t"
+        "subc.u32 t44, t41, 0x0;\n\t"
+        "add.cc.u32 t45, t25, t44;\n\t"
+        "addc.cc.u32 t46, t26, 0x0;\n\t"
+        "addc.cc.u32 t47, t27, 0x0;\n\t"
+        "addc.cc.u32 t48, t36, 0x0;\n\t"
+        "addc.cc.u32 t49, t37, 0x0;\n\t"
+        "addc.cc.u32 t50, t38, 0x0;\n\t"
+        "addc.cc.u32 t51, t42, 0x0;\n\t"
+        "addc.cc.u32 t52, t43, 0x0;\n\t"
+        "addc.u32 t53, 0x0, 0x0;\n\t"
+        "add.cc.u32 t54, t52, t44;\n\t"
+        "addc.u32 t55, t53, 0x0;\n\t"
+        "sub.cc.u32 t56, t48, t44;\n\t"
+        "subc.cc.u32 t57, t49, 0x0;\n\t"
+        "subc.cc.u32 t58, t50, 0x0;\n\t"
+        "subc.cc.u32 t59, t51, 0x0;\n\t"
+        "subc.cc.u32 t60, t54, 0x0;\n\t"
+        "subc.u32 t61, t55, 0x0;\n\t"
+        "sub.cc.u32 t62, t59, t44;\n\t"
+        "subc.cc.u32 t63, t60, 0x0;\n\t"
+        "subc.u32 t64, t61, 0x0;\n\t"
+        "add.cc.u32 t65, t45, t64;\n\t"
+        "addc.cc.u32 t66, t46, 0x0;\n\t"
+        "addc.cc.u32 t67, t47, 0x0;\n\t"
+        "addc.cc.u32 t68, t56, 0x0;\n\t"
+        "addc.cc.u32 t69, t57, 0x0;\n\t"
+        "addc.cc.u32 t70, t58, 0x0;\n\t"
+        "addc.cc.u32 t71, t62, 0x0;\n\t"
+        "addc.cc.u32 t72, t63, 0x0;\n\t"
+        "addc.u32 t73, 0x0, 0x0;\n\t"
+        "add.cc.u32 t74, t72, t64;\n\t"
+        "addc.u32 t75, t73, 0x0;\n\t"
+        "sub.cc.u32 t76, t68, t64;\n\t"
+        "subc.cc.u32 t77, t69, 0x0;\n\t"
+        "subc.cc.u32 t78, t70, 0x0;\n\t"
+        "subc.cc.u32 t79, t71, 0x0;\n\t"
+        "subc.cc.u32 t80, t74, 0x0;\n\t"
+        "subc.u32 t81, t75, 0x0;\n\t"
+        "sub.cc.u32 t82, t79, t64;\n\t"
+        "subc.cc.u32 t83, t80, 0x0;\n\t"
+        "subc.u32 t84, t81, 0x0;\n\t"
+        "sub.cc.u32 t85, t65, 0xffffffff;\n\t"
+        "subc.cc.u32 t86, t66, 0xffffffff;\n\t"
+        "subc.cc.u32 t87, t67, 0xffffffff;\n\t"
+        "subc.cc.u32 t88, t76, 0x0;\n\t"
+        "subc.cc.u32 t89, t77, 0x0;\n\t"
+        "subc.cc.u32 t90, t78, 0x0;\n\t"
+        "subc.cc.u32 t91, t82, 0x1;\n\t"
+        "subc.cc.u32 t92, t83, 0xffffffff;\n\t"
+        "subc.cc.u32 t93, t84, 0x0;\n\t"
+        "subc.u32 t94, 0x0, 0x0;\n\t"
+        "xor.b32 t95, t85, t65;\n\t"
+        "and.b32 t96, t95, t94;\n\t"
+        "xor.b32 t97, t96, t85;\n\t"
+        "xor.b32 t98, t86, t66;\n\t"
+        "and.b32 t99, t98, t94;\n\t"
+        "xor.b32 t100, t99, t86;\n\t"
+        "xor.b32 t101, t87, t67;\n\t"
+        "and.b32 t102, t101, t94;\n\t"
+        "xor.b32 t103, t102, t87;\n\t"
+        "xor.b32 t104, t88, t76;\n\t"
+        "and.b32 t105, t104, t94;\n\t"
+        "xor.b32 t106, t105, t88;\n\t"
+        "xor.b32 t107, t89, t77;\n\t"
+        "and.b32 t108, t107, t94;\n\t"
+        "xor.b32 t109, t108, t89;\n\t"
+        "xor.b32 t110, t90, t78;\n\t"
+        "and.b32 t111, t110, t94;\n\t"
+        "xor.b32 t112, t111, t90;\n\t"
+        "xor.b32 t113, t91, t82;\n\t"
+        "and.b32 t114, t113, t94;\n\t"
+        "xor.b32 t115, t114, t91;\n\t"
+        "xor.b32 t116, t92, t83;\n\t"
+        "and.b32 t117, t116, t94;\n\t"
+        "xor.b32 t118, t117, t92;\n\t"
+        "mov.u32 %0, t97;\n\t"
+        "mov.u32 %1, t100;\n\t"
+        "mov.u32 %2, t103;\n\t"
+        "mov.u32 %3, t106;\n\t"
+        "mov.u32 %4, t109;\n\t"
+        "mov.u32 %5, t112;\n\t"
+        "mov.u32 %6, t115;\n\t"
+        "mov.u32 %7, t118;\n\t"
+        "}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(b));
+#else
+    const uint32_t a_0_i = a[0];
+    const uint32_t a_1_i = a[1];
+    const uint32_t a_2_i = a[2];
+    const uint32_t a_3_i = a[3];
+    const uint32_t a_4_i = a[4];
+    const uint32_t a_5_i = a[5];
+    const uint32_t a_6_i = a[6];
+    const uint32_t a_7_i = a[7];
+    const uint32_t c_0_i = c[0];
+    const uint32_t c_1_i = c[1];
+    const uint32_t c_2_i = c[2];
+    const uint32_t c_3_i = c[3];
+    const uint32_t c_4_i = c[4];
+    const uint32_t c_5_i = c[5];
+    const uint32_t c_6_i = c[6];
+    const uint32_t c_7_i = c[7];
+    const uint32_t b_i = b;
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18, t19, t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31, t32, t33, t34, t35, t36, t37, t38, t39, t40, t41, t42, t43, t44, t45, t46, t47, t48, t49, t50, t51, t52, t53, t54, t55, t56, t57, t58, t59, t60, t61, t62, t63, t64, t65, t66, t67, t68, t69, t70, t71, t72, t73, t74, t75, t76, t77, t78, t79, t80, t81, t82, t83, t84, t85, t86, t87, t88, t89, t90, t91, t92, t93, t94, t95, t96, t97, t98, t99, t100, t101, t102, t103, t104, t105, t106, t107, t108, t109, t110, t111, t112, t113, t114, t115, t116, t117, t118;
+    uint64_t w_; uint32_t cf_ = 0; (void)cf_; (void)w_;
+    w_ = (uint64_t)(uint32_t)(a_0_i * b_i) + c_0_i; t0 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_0_i * b_i) >> 32) + c_1_i + cf_; t1 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_2_i * b_i) + c_2_i + cf_; t2 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_2_i * b_i) >> 32) + c_3_i + cf_; t3 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_4_i * b_i) + c_4_i + cf_; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_4_i * b_i) >> 32) + c_5_i + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_6_i * b_i) + c_6_i + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_6_i * b_i) >> 32) + c_7_i + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t8 = (uint32_t)w_;
+    t9 = (uint32_t)((uint32_t)(a_1_i * b_i));
+    t10 = (uint32_t)(((uint64_t)a_1_i * b_i) >> 32);
+    t11 = (uint32_t)((uint32_t)(a_3_i * b_i));
+    t12 = (uint32_t)(((uint64_t)a_3_i * b_i) >> 32);
+    t13 = (uint32_t)((uint32_t)(a_5_i * b_i));
+    t14 = (uint32_t)(((uint64_t)a_5_i * b_i) >> 32);
+    t15 = (uint32_t)((uint32_t)(a_7_i * b_i));
+    t16 = (uint32_t)(((uint64_t)a_7_i * b_i) >> 32);
+    w_ = (uint64_t)t1 + t9; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t2 + t10 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t3 + t11 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t4 + t12 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t5 + t13 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t6 + t14 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t7 + t15 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t8 + t16 + cf_; t24 = (uint32_t)w_;
+    w_ = (uint64_t)t0 + t24; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t17 + 0x0u + cf_; t26 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t18 + 0x0u + cf_; t27 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t19 + 0x0u + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t20 + 0x0u + cf_; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t21 + 0x0u + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t22 + 0x0u + cf_; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t23 + 0x0u + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t33 = (uint32_t)w_;
+    w_ = (uint64_t)t32 + t24; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t33 + 0x0u + cf_; t35 = (uint32_t)w_;
+    w_ = (uint64_t)t28 - t24; t36 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t29 - 0x0u - cf_; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t30 - 0x0u - cf_; t38 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t31 - 0x0u - cf_; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t34 - 0x0u - cf_; t40 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t35 - 0x0u - cf_; t41 = (uint32_t)w_;
+    w_ = (uint64_t)t39 - t24; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t40 - 0x0u - cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t41 - 0x0u - cf_; t44 = (uint32_t)w_;
+    w_ = (uint64_t)t25 + t44; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t26 + 0x0u + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t27 + 0x0u + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t36 + 0x0u + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t37 + 0x0u + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t38 + 0x0u + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t42 + 0x0u + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t43 + 0x0u + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t53 = (uint32_t)w_;
+    w_ = (uint64_t)t52 + t44; t54 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t53 + 0x0u + cf_; t55 = (uint32_t)w_;
+    w_ = (uint64_t)t48 - t44; t56 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t49 - 0x0u - cf_; t57 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t50 - 0x0u - cf_; t58 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t51 - 0x0u - cf_; t59 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t54 - 0x0u - cf_; t60 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t55 - 0x0u - cf_; t61 = (uint32_t)w_;
+    w_ = (uint64_t)t59 - t44; t62 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t60 - 0x0u - cf_; t63 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t61 - 0x0u - cf_; t64 = (uint32_t)w_;
+    w_ = (uint64_t)t45 + t64; t65 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t46 + 0x0u + cf_; t66 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t47 + 0x0u + cf_; t67 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t56 + 0x0u + cf_; t68 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t57 + 0x0u + cf_; t69 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t58 + 0x0u + cf_; t70 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t62 + 0x0u + cf_; t71 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t63 + 0x0u + cf_; t72 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t73 = (uint32_t)w_;
+    w_ = (uint64_t)t72 + t64; t74 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t73 + 0x0u + cf_; t75 = (uint32_t)w_;
+    w_ = (uint64_t)t68 - t64; t76 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t69 - 0x0u - cf_; t77 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t70 - 0x0u - cf_; t78 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t71 - 0x0u - cf_; t79 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t74 - 0x0u - cf_; t80 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t75 - 0x0u - cf_; t81 = (uint32_t)w_;
+    w_ = (uint64_t)t79 - t64; t82 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t80 - 0x0u - cf_; t83 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t81 - 0x0u - cf_; t84 = (uint32_t)w_;
+    w_ = (uint64_t)t65 - 0xffffffffu; t85 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t66 - 0xffffffffu - cf_; t86 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t67 - 0xffffffffu - cf_; t87 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t76 - 0x0u - cf_; t88 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t77 - 0x0u - cf_; t89 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t78 - 0x0u - cf_; t90 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t82 - 0x1u - cf_; t91 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t83 - 0xffffffffu - cf_; t92 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t84 - 0x0u - cf_; t93 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)0x0u - 0x0u - cf_; t94 = (uint32_t)w_;
+    t95 = (uint32_t)(t85 ^ t65);
+    t96 = (uint32_t)(t95 & t94);
+    t97 = (uint32_t)(t96 ^ t85);
+    t98 = (uint32_t)(t86 ^ t66);
+    t99 = (uint32_t)(t98 & t94);
+    t100 = (uint32_t)(t99 ^ t86);
+    t101 = (uint32_t)(t87 ^ t67);
+    t102 = (uint32_t)(t101 & t94);
+    t103 = (uint32_t)(t102 ^ t87);
+    t104 = (uint32_t)(t88 ^ t76);
+    t105 = (uint32_t)(t104 & t94);
+    t106 = (uint32_t)(t105 ^ t88);
+    t107 = (uint32_t)(t89 ^ t77);
+    t108 = (uint32_t)(t107 & t94);
+    t109 = (uint32_t)(t108 ^ t89);
+    t110 = (uint32_t)(t90 ^ t78);
+    t111 = (uint32_t)(t110 & t94);
+    t112 = (uint32_t)(t111 ^ t90);
+    t113 = (uint32_t)(t91 ^ t82);
+    t114 = (uint32_t)(t113 & t94);
+    t115 = (uint32_t)(t114 ^ t91);
+    t116 = (uint32_t)(t92 ^ t83);
+    t117 = (uint32_t)(t116 & t94);
+    t118 = (uint32_t)(t117 ^ t92);
+    r[0] = t97;
+    r[1] = t100;
+    r[2] = t103;
+    r[3] = t106;
+    r[4] = t109;
+    r[5] = t112;
+    r[6] = t115;
+    r[7] = t118;
 #endif
   }
 

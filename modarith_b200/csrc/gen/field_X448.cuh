@@ -2,9 +2,10 @@
 // Command line : python -m modarith_b200.gen.monty_sm100 X448
 // modulus X448 = 0xfffffffffffffffffffffffffffffffffffffffffffffffffffffffeffffffffffffffffffffffffffffffffffffffffffffffffffffffff
 // plan GenMersenne: 14 saturated 32-bit limbs; stored values < 2^448; R = 2^0
-//   mul   : 196 IMAD.WIDE   0 IMAD  ~113 ALU-pipe ops
-//   sqr   : 105 IMAD.WIDE   0 IMAD  ~137 ALU-pipe ops
+//   mul   : 196 IMAD.WIDE   0 IMAD  ~101 ALU-pipe ops
+//   sqr   : 105 IMAD.WIDE   0 IMAD  ~125 ALU-pipe ops
 //   mli   :  14 IMAD.WIDE   0 IMAD  ~ 38 ALU-pipe ops
+//   mla   :  14 IMAD.WIDE   0 IMAD  ~ 39 ALU-pipe ops
 //   add   :   0 IMAD.WIDE   0 IMAD  ~ 38 ALU-pipe ops
 //   sub   :   0 IMAD.WIDE   0 IMAD  ~ 46 ALU-pipe ops
 //   canon :   0 IMAD.WIDE   0 IMAD  ~ 58 ALU-pipe ops
@@ -19,6 +20,7 @@ struct F_X448 {
   static constexpr int PM1D2 = 1;
   static constexpr bool MONTGOMERY = false;
   static constexpr int PRO_SQR = 445, PRO_MUL = 14;
+  static constexpr int LADDER_MINBLOCKS = 2;   // resident 128-thread CTAs per SM for k_rfc7748
   static constexpr bool HAS_CURVE = true;
   static constexpr uint32_t A24 = 39081;
   static constexpr int COF = 2;
@@ -71,8 +73,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t12, %25, %29, t12;\n\t"
         "madc.hi.cc.u32 t13, %25, %29, t13;\n\t"
         "madc.lo.cc.u32 t14, %27, %29, 0x0;\n\t"
-        "madc.hi.cc.u32 t15, %27, %29, 0x0;\n\t"
-        "addc.u32 t16, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t15, %27, %29, 0x0;\n\t"
         "mad.lo.cc.u32 t29, %14, %29, t29;\n\t"
         "madc.hi.cc.u32 t30, %14, %29, t30;\n\t"
         "madc.lo.cc.u32 t31, %16, %29, t31;\n\t"
@@ -102,7 +103,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t13, %24, %30, t13;\n\t"
         "madc.lo.cc.u32 t14, %26, %30, t14;\n\t"
         "madc.hi.cc.u32 t15, %26, %30, t15;\n\t"
-        "addc.u32 t16, t16, 0x0;\n\t"
+        "addc.u32 t16, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t31, %15, %30, t31;\n\t"
         "madc.hi.cc.u32 t32, %15, %30, t32;\n\t"
         "madc.lo.cc.u32 t33, %17, %30, t33;\n\t"
@@ -116,8 +117,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t41, %25, %30, t41;\n\t"
         "madc.hi.cc.u32 t42, %25, %30, t42;\n\t"
         "madc.lo.cc.u32 t43, %27, %30, t43;\n\t"
-        "madc.hi.cc.u32 t44, %27, %30, 0x0;\n\t"
-        "addc.u32 t45, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t44, %27, %30, 0x0;\n\t"
         "mad.lo.cc.u32 t4, %15, %31, t4;\n\t"
         "madc.hi.cc.u32 t5, %15, %31, t5;\n\t"
         "madc.lo.cc.u32 t6, %17, %31, t6;\n\t"
@@ -131,8 +131,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t14, %25, %31, t14;\n\t"
         "madc.hi.cc.u32 t15, %25, %31, t15;\n\t"
         "madc.lo.cc.u32 t16, %27, %31, t16;\n\t"
-        "madc.hi.cc.u32 t17, %27, %31, 0x0;\n\t"
-        "addc.u32 t18, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t17, %27, %31, 0x0;\n\t"
         "mad.lo.cc.u32 t31, %14, %31, t31;\n\t"
         "madc.hi.cc.u32 t32, %14, %31, t32;\n\t"
         "madc.lo.cc.u32 t33, %16, %31, t33;\n\t"
@@ -147,7 +146,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t42, %24, %31, t42;\n\t"
         "madc.lo.cc.u32 t43, %26, %31, t43;\n\t"
         "madc.hi.cc.u32 t44, %26, %31, t44;\n\t"
-        "addc.u32 t45, t45, 0x0;\n\t"
+        "addc.u32 t45, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t4, %14, %32, t4;\n\t"
         "madc.hi.cc.u32 t5, %14, %32, t5;\n\t"
         "madc.lo.cc.u32 t6, %16, %32, t6;\n\t"
@@ -162,7 +161,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t15, %24, %32, t15;\n\t"
         "madc.lo.cc.u32 t16, %26, %32, t16;\n\t"
         "madc.hi.cc.u32 t17, %26, %32, t17;\n\t"
-        "addc.u32 t18, t18, 0x0;\n\t"
+        "addc.u32 t18, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t33, %15, %32, t33;\n\t"
         "madc.hi.cc.u32 t34, %15, %32, t34;\n\t"
         "madc.lo.cc.u32 t35, %17, %32, t35;\n\t"
@@ -176,8 +175,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t43, %25, %32, t43;\n\t"
         "madc.hi.cc.u32 t44, %25, %32, t44;\n\t"
         "madc.lo.cc.u32 t45, %27, %32, t45;\n\t"
-        "madc.hi.cc.u32 t46, %27, %32, 0x0;\n\t"
-        "addc.u32 t47, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t46, %27, %32, 0x0;\n\t"
         "mad.lo.cc.u32 t6, %15, %33, t6;\n\t"
         "madc.hi.cc.u32 t7, %15, %33, t7;\n\t"
         "madc.lo.cc.u32 t8, %17, %33, t8;\n\t"
@@ -191,8 +189,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t16, %25, %33, t16;\n\t"
         "madc.hi.cc.u32 t17, %25, %33, t17;\n\t"
         "madc.lo.cc.u32 t18, %27, %33, t18;\n\t"
-        "madc.hi.cc.u32 t19, %27, %33, 0x0;\n\t"
-        "addc.u32 t20, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t19, %27, %33, 0x0;\n\t"
         "mad.lo.cc.u32 t33, %14, %33, t33;\n\t"
         "madc.hi.cc.u32 t34, %14, %33, t34;\n\t"
         "madc.lo.cc.u32 t35, %16, %33, t35;\n\t"
@@ -207,7 +204,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t44, %24, %33, t44;\n\t"
         "madc.lo.cc.u32 t45, %26, %33, t45;\n\t"
         "madc.hi.cc.u32 t46, %26, %33, t46;\n\t"
-        "addc.u32 t47, t47, 0x0;\n\t"
+        "addc.u32 t47, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t6, %14, %34, t6;\n\t"
         "madc.hi.cc.u32 t7, %14, %34, t7;\n\t"
         "madc.lo.cc.u32 t8, %16, %34, t8;\n\t"
@@ -222,7 +219,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t17, %24, %34, t17;\n\t"
         "madc.lo.cc.u32 t18, %26, %34, t18;\n\t"
         "madc.hi.cc.u32 t19, %26, %34, t19;\n\t"
-        "addc.u32 t20, t20, 0x0;\n\t"
+        "addc.u32 t20, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t35, %15, %34, t35;\n\t"
         "madc.hi.cc.u32 t36, %15, %34, t36;\n\t"
         "madc.lo.cc.u32 t37, %17, %34, t37;\n\t"
@@ -236,8 +233,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t45, %25, %34, t45;\n\t"
         "madc.hi.cc.u32 t46, %25, %34, t46;\n\t"
         "madc.lo.cc.u32 t47, %27, %34, t47;\n\t"
-        "madc.hi.cc.u32 t48, %27, %34, 0x0;\n\t"
-        "addc.u32 t49, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t48, %27, %34, 0x0;\n\t"
         "mad.lo.cc.u32 t8, %15, %35, t8;\n\t"
         "madc.hi.cc.u32 t9, %15, %35, t9;\n\t"
         "madc.lo.cc.u32 t10, %17, %35, t10;\n\t"
@@ -251,8 +247,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t18, %25, %35, t18;\n\t"
         "madc.hi.cc.u32 t19, %25, %35, t19;\n\t"
         "madc.lo.cc.u32 t20, %27, %35, t20;\n\t"
-        "madc.hi.cc.u32 t21, %27, %35, 0x0;\n\t"
-        "addc.u32 t22, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t21, %27, %35, 0x0;\n\t"
         "mad.lo.cc.u32 t35, %14, %35, t35;\n\t"
         "madc.hi.cc.u32 t36, %14, %35, t36;\n\t"
         "madc.lo.cc.u32 t37, %16, %35, t37;\n\t"
@@ -267,7 +262,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t46, %24, %35, t46;\n\t"
         "madc.lo.cc.u32 t47, %26, %35, t47;\n\t"
         "madc.hi.cc.u32 t48, %26, %35, t48;\n\t"
-        "addc.u32 t49, t49, 0x0;\n\t"
+        "addc.u32 t49, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t8, %14, %36, t8;\n\t"
         "madc.hi.cc.u32 t9, %14, %36, t9;\n\t"
         "madc.lo.cc.u32 t10, %16, %36, t10;\n\t"
@@ -282,7 +277,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t19, %24, %36, t19;\n\t"
         "madc.lo.cc.u32 t20, %26, %36, t20;\n\t"
         "madc.hi.cc.u32 t21, %26, %36, t21;\n\t"
-        "addc.u32 t22, t22, 0x0;\n\t"
+        "addc.u32 t22, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t37, %15, %36, t37;\n\t"
         "madc.hi.cc.u32 t38, %15, %36, t38;\n\t"
         "madc.lo.cc.u32 t39, %17, %36, t39;\n\t"
@@ -296,8 +291,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t47, %25, %36, t47;\n\t"
         "madc.hi.cc.u32 t48, %25, %36, t48;\n\t"
         "madc.lo.cc.u32 t49, %27, %36, t49;\n\t"
-        "madc.hi.cc.u32 t50, %27, %36, 0x0;\n\t"
-        "addc.u32 t51, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t50, %27, %36, 0x0;\n\t"
         "mad.lo.cc.u32 t10, %15, %37, t10;\n\t"
         "madc.hi.cc.u32 t11, %15, %37, t11;\n\t"
         "madc.lo.cc.u32 t12, %17, %37, t12;\n\t"
@@ -311,8 +305,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t20, %25, %37, t20;\n\t"
         "madc.hi.cc.u32 t21, %25, %37, t21;\n\t"
         "madc.lo.cc.u32 t22, %27, %37, t22;\n\t"
-        "madc.hi.cc.u32 t23, %27, %37, 0x0;\n\t"
-        "addc.u32 t24, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t23, %27, %37, 0x0;\n\t"
         "mad.lo.cc.u32 t37, %14, %37, t37;\n\t"
         "madc.hi.cc.u32 t38, %14, %37, t38;\n\t"
         "madc.lo.cc.u32 t39, %16, %37, t39;\n\t"
@@ -327,7 +320,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t48, %24, %37, t48;\n\t"
         "madc.lo.cc.u32 t49, %26, %37, t49;\n\t"
         "madc.hi.cc.u32 t50, %26, %37, t50;\n\t"
-        "addc.u32 t51, t51, 0x0;\n\t"
+        "addc.u32 t51, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t10, %14, %38, t10;\n\t"
         "madc.hi.cc.u32 t11, %14, %38, t11;\n\t"
         "madc.lo.cc.u32 t12, %16, %38, t12;\n\t"
@@ -342,7 +335,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t21, %24, %38, t21;\n\t"
         "madc.lo.cc.u32 t22, %26, %38, t22;\n\t"
         "madc.hi.cc.u32 t23, %26, %38, t23;\n\t"
-        "addc.u32 t24, t24, 0x0;\n\t"
+        "addc.u32 t24, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t39, %15, %38, t39;\n\t"
         "madc.hi.cc.u32 t40, %15, %38, t40;\n\t"
         "madc.lo.cc.u32 t41, %17, %38, t41;\n\t"
@@ -356,8 +349,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t49, %25, %38, t49;\n\t"
         "madc.hi.cc.u32 t50, %25, %38, t50;\n\t"
         "madc.lo.cc.u32 t51, %27, %38, t51;\n\t"
-        "madc.hi.cc.u32 t52, %27, %38, 0x0;\n\t"
-        "addc.u32 t53, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t52, %27, %38, 0x0;\n\t"
         "mad.lo.cc.u32 t12, %15, %39, t12;\n\t"
         "madc.hi.cc.u32 t13, %15, %39, t13;\n\t"
         "madc.lo.cc.u32 t14, %17, %39, t14;\n\t"
@@ -371,8 +363,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t22, %25, %39, t22;\n\t"
         "madc.hi.cc.u32 t23, %25, %39, t23;\n\t"
         "madc.lo.cc.u32 t24, %27, %39, t24;\n\t"
-        "madc.hi.cc.u32 t25, %27, %39, 0x0;\n\t"
-        "addc.u32 t26, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t25, %27, %39, 0x0;\n\t"
         "mad.lo.cc.u32 t39, %14, %39, t39;\n\t"
         "madc.hi.cc.u32 t40, %14, %39, t40;\n\t"
         "madc.lo.cc.u32 t41, %16, %39, t41;\n\t"
@@ -387,7 +378,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t50, %24, %39, t50;\n\t"
         "madc.lo.cc.u32 t51, %26, %39, t51;\n\t"
         "madc.hi.cc.u32 t52, %26, %39, t52;\n\t"
-        "addc.u32 t53, t53, 0x0;\n\t"
+        "addc.u32 t53, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t12, %14, %40, t12;\n\t"
         "madc.hi.cc.u32 t13, %14, %40, t13;\n\t"
         "madc.lo.cc.u32 t14, %16, %40, t14;\n\t"
@@ -402,7 +393,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t23, %24, %40, t23;\n\t"
         "madc.lo.cc.u32 t24, %26, %40, t24;\n\t"
         "madc.hi.cc.u32 t25, %26, %40, t25;\n\t"
-        "addc.u32 t26, t26, 0x0;\n\t"
+        "addc.u32 t26, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t41, %15, %40, t41;\n\t"
         "madc.hi.cc.u32 t42, %15, %40, t42;\n\t"
         "madc.lo.cc.u32 t43, %17, %40, t43;\n\t"
@@ -416,8 +407,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t51, %25, %40, t51;\n\t"
         "madc.hi.cc.u32 t52, %25, %40, t52;\n\t"
         "madc.lo.cc.u32 t53, %27, %40, t53;\n\t"
-        "madc.hi.cc.u32 t54, %27, %40, 0x0;\n\t"
-        "addc.u32 t55, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t54, %27, %40, 0x0;\n\t"
         "mad.lo.cc.u32 t14, %15, %41, t14;\n\t"
         "madc.hi.cc.u32 t15, %15, %41, t15;\n\t"
         "madc.lo.cc.u32 t16, %17, %41, t16;\n\t"
@@ -446,7 +436,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t52, %24, %41, t52;\n\t"
         "madc.lo.cc.u32 t53, %26, %41, t53;\n\t"
         "madc.hi.cc.u32 t54, %26, %41, t54;\n\t"
-        "addc.u32 t55, t55, 0x0;\n\t"
+        "addc.u32 t55, 0x0, 0x0;\n\t"
         "add.cc.u32 t56, t1, t29;\n\t"
         "addc.cc.u32 t57, t2, t30;\n\t"
         "addc.cc.u32 t58, t3, t31;\n\t"
@@ -624,8 +614,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_1_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_1_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_1_i) + 0x0u + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_1_i) >> 32) + 0x0u + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t16 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_1_i) >> 32) + 0x0u + cf_; t15 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_1_i) + t29; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_1_i) >> 32) + t30 + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_1_i) + t31 + cf_; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -655,7 +644,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_2_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_2_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_2_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t16 + 0x0u + cf_; t16 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t16 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_2_i) + t31; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_2_i) >> 32) + t32 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_2_i) + t33 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -669,8 +658,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_2_i) + t41 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_2_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_2_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_2_i) >> 32) + 0x0u + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t45 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_2_i) >> 32) + 0x0u + cf_; t44 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_3_i) + t4; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_3_i) >> 32) + t5 + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_3_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -684,8 +672,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_3_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_3_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_3_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_3_i) >> 32) + 0x0u + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t18 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_3_i) >> 32) + 0x0u + cf_; t17 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_3_i) + t31; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_3_i) >> 32) + t32 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_3_i) + t33 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -700,7 +687,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_3_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_3_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_3_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t45 + 0x0u + cf_; t45 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t45 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_4_i) + t4; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_4_i) >> 32) + t5 + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_4_i) + t6 + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -715,7 +702,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_4_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_4_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_4_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t18 + 0x0u + cf_; t18 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t18 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_4_i) + t33; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_4_i) >> 32) + t34 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_4_i) + t35 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -729,8 +716,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_4_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_4_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_4_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_4_i) >> 32) + 0x0u + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t47 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_4_i) >> 32) + 0x0u + cf_; t46 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_5_i) + t6; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_5_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_5_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -744,8 +730,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_5_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_5_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_5_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_5_i) >> 32) + 0x0u + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t20 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_5_i) >> 32) + 0x0u + cf_; t19 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_5_i) + t33; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_5_i) >> 32) + t34 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_5_i) + t35 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -760,7 +745,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_5_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_5_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_5_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t47 + 0x0u + cf_; t47 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t47 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_6_i) + t6; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_6_i) >> 32) + t7 + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_6_i) + t8 + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -775,7 +760,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_6_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_6_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_6_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t20 + 0x0u + cf_; t20 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t20 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_6_i) + t35; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_6_i) >> 32) + t36 + cf_; t36 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_6_i) + t37 + cf_; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -789,8 +774,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_6_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_6_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_6_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_6_i) >> 32) + 0x0u + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t49 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_6_i) >> 32) + 0x0u + cf_; t48 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_7_i) + t8; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_7_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_7_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -804,8 +788,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_7_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_7_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_7_i) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_7_i) >> 32) + 0x0u + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t22 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_7_i) >> 32) + 0x0u + cf_; t21 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_7_i) + t35; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_7_i) >> 32) + t36 + cf_; t36 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_7_i) + t37 + cf_; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -820,7 +803,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_7_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_7_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_7_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t49 + 0x0u + cf_; t49 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t49 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_8_i) + t8; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_8_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_8_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -835,7 +818,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_8_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_8_i) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_8_i) >> 32) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t22 + 0x0u + cf_; t22 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t22 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_8_i) + t37; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_8_i) >> 32) + t38 + cf_; t38 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_8_i) + t39 + cf_; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -849,8 +832,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_8_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_8_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_8_i) + t49 + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_8_i) >> 32) + 0x0u + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t51 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_8_i) >> 32) + 0x0u + cf_; t50 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_9_i) + t10; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_9_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_9_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -864,8 +846,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_9_i) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_9_i) >> 32) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_9_i) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_9_i) >> 32) + 0x0u + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t24 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_9_i) >> 32) + 0x0u + cf_; t23 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_9_i) + t37; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_9_i) >> 32) + t38 + cf_; t38 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_9_i) + t39 + cf_; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -880,7 +861,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_9_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_9_i) + t49 + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_9_i) >> 32) + t50 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t51 + 0x0u + cf_; t51 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t51 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_10_i) + t10; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_10_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_10_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -895,7 +876,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_10_i) >> 32) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_10_i) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_10_i) >> 32) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t24 + 0x0u + cf_; t24 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t24 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_10_i) + t39; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_10_i) >> 32) + t40 + cf_; t40 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_10_i) + t41 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -909,8 +890,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_10_i) + t49 + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_10_i) >> 32) + t50 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_10_i) + t51 + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_10_i) >> 32) + 0x0u + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t53 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_10_i) >> 32) + 0x0u + cf_; t52 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_11_i) + t12; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_11_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_11_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -924,8 +904,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_11_i) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_11_i) >> 32) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_11_i) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_11_i) >> 32) + 0x0u + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t26 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_11_i) >> 32) + 0x0u + cf_; t25 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_11_i) + t39; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_11_i) >> 32) + t40 + cf_; t40 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_11_i) + t41 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -940,7 +919,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_11_i) >> 32) + t50 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_11_i) + t51 + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_11_i) >> 32) + t52 + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t53 + 0x0u + cf_; t53 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t53 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_0_i * b_12_i) + t12; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_0_i * b_12_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * b_12_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -955,7 +934,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_12_i) >> 32) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_12_i) + t24 + cf_; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_12_i) >> 32) + t25 + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t26 + 0x0u + cf_; t26 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t26 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_12_i) + t41; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_12_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_12_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -969,8 +948,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_11_i * b_12_i) + t51 + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * b_12_i) >> 32) + t52 + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_13_i * b_12_i) + t53 + cf_; t53 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_13_i * b_12_i) >> 32) + 0x0u + cf_; t54 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t55 = (uint32_t)w_;
+    w_ = (((uint64_t)a_13_i * b_12_i) >> 32) + 0x0u + cf_; t54 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * b_13_i) + t14; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * b_13_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * b_13_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -999,7 +977,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_10_i * b_13_i) >> 32) + t52 + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_12_i * b_13_i) + t53 + cf_; t53 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_12_i * b_13_i) >> 32) + t54 + cf_; t54 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t55 + 0x0u + cf_; t55 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t55 = (uint32_t)w_;
     w_ = (uint64_t)t1 + t29; t56 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t2 + t30 + cf_; t57 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t31 + cf_; t58 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1147,8 +1125,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t12, %15, %25, t12;\n\t"
         "madc.hi.cc.u32 t13, %15, %25, t13;\n\t"
         "madc.lo.cc.u32 t14, %15, %27, 0x0;\n\t"
-        "madc.hi.cc.u32 t15, %15, %27, 0x0;\n\t"
-        "addc.u32 t16, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t15, %15, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t31, %15, %16, t31;\n\t"
         "madc.hi.cc.u32 t32, %15, %16, t32;\n\t"
         "madc.lo.cc.u32 t33, %15, %18, t33;\n\t"
@@ -1172,7 +1149,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t13, %16, %24, t13;\n\t"
         "madc.lo.cc.u32 t14, %16, %26, t14;\n\t"
         "madc.hi.cc.u32 t15, %16, %26, t15;\n\t"
-        "addc.u32 t16, t16, 0x0;\n\t"
+        "addc.u32 t16, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t33, %16, %17, t33;\n\t"
         "madc.hi.cc.u32 t34, %16, %17, t34;\n\t"
         "madc.lo.cc.u32 t35, %16, %19, t35;\n\t"
@@ -1184,8 +1161,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t41, %16, %25, t41;\n\t"
         "madc.hi.cc.u32 t42, %16, %25, t42;\n\t"
         "madc.lo.cc.u32 t43, %16, %27, t43;\n\t"
-        "madc.hi.cc.u32 t44, %16, %27, 0x0;\n\t"
-        "addc.u32 t45, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t44, %16, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t8, %17, %19, t8;\n\t"
         "madc.hi.cc.u32 t9, %17, %19, t9;\n\t"
         "madc.lo.cc.u32 t10, %17, %21, t10;\n\t"
@@ -1195,8 +1171,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t14, %17, %25, t14;\n\t"
         "madc.hi.cc.u32 t15, %17, %25, t15;\n\t"
         "madc.lo.cc.u32 t16, %17, %27, t16;\n\t"
-        "madc.hi.cc.u32 t17, %17, %27, 0x0;\n\t"
-        "addc.u32 t18, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t17, %17, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t35, %17, %18, t35;\n\t"
         "madc.hi.cc.u32 t36, %17, %18, t36;\n\t"
         "madc.lo.cc.u32 t37, %17, %20, t37;\n\t"
@@ -1207,7 +1182,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t42, %17, %24, t42;\n\t"
         "madc.lo.cc.u32 t43, %17, %26, t43;\n\t"
         "madc.hi.cc.u32 t44, %17, %26, t44;\n\t"
-        "addc.u32 t45, t45, 0x0;\n\t"
+        "addc.u32 t45, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t10, %18, %20, t10;\n\t"
         "madc.hi.cc.u32 t11, %18, %20, t11;\n\t"
         "madc.lo.cc.u32 t12, %18, %22, t12;\n\t"
@@ -1216,7 +1191,7 @@ struct F_X448 {
         "madc.hi.cc.u32 t15, %18, %24, t15;\n\t"
         "madc.lo.cc.u32 t16, %18, %26, t16;\n\t"
         "madc.hi.cc.u32 t17, %18, %26, t17;\n\t"
-        "addc.u32 t18, t18, 0x0;\n\t"
+        "addc.u32 t18, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t37, %18, %19, t37;\n\t"
         "madc.hi.cc.u32 t38, %18, %19, t38;\n\t"
         "madc.lo.cc.u32 t39, %18, %21, t39;\n\t"
@@ -1226,8 +1201,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t43, %18, %25, t43;\n\t"
         "madc.hi.cc.u32 t44, %18, %25, t44;\n\t"
         "madc.lo.cc.u32 t45, %18, %27, t45;\n\t"
-        "madc.hi.cc.u32 t46, %18, %27, 0x0;\n\t"
-        "addc.u32 t47, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t46, %18, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t12, %19, %21, t12;\n\t"
         "madc.hi.cc.u32 t13, %19, %21, t13;\n\t"
         "madc.lo.cc.u32 t14, %19, %23, t14;\n\t"
@@ -1235,8 +1209,7 @@ struct F_X448 {
         "madc.lo.cc.u32 t16, %19, %25, t16;\n\t"
         "madc.hi.cc.u32 t17, %19, %25, t17;\n\t"
         "madc.lo.cc.u32 t18, %19, %27, t18;\n\t"
-        "madc.hi.cc.u32 t19, %19, %27, 0x0;\n\t"
-        "addc.u32 t20, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t19, %19, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t39, %19, %20, t39;\n\t"
         "madc.hi.cc.u32 t40, %19, %20, t40;\n\t"
         "madc.lo.cc.u32 t41, %19, %22, t41;\n\t"
@@ -1245,14 +1218,14 @@ struct F_X448 {
         "madc.hi.cc.u32 t44, %19, %24, t44;\n\t"
         "madc.lo.cc.u32 t45, %19, %26, t45;\n\t"
         "madc.hi.cc.u32 t46, %19, %26, t46;\n\t"
-        "addc.u32 t47, t47, 0x0;\n\t"
+        "addc.u32 t47, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t14, %20, %22, t14;\n\t"
         "madc.hi.cc.u32 t15, %20, %22, t15;\n\t"
         "madc.lo.cc.u32 t16, %20, %24, t16;\n\t"
         "madc.hi.cc.u32 t17, %20, %24, t17;\n\t"
         "madc.lo.cc.u32 t18, %20, %26, t18;\n\t"
         "madc.hi.cc.u32 t19, %20, %26, t19;\n\t"
-        "addc.u32 t20, t20, 0x0;\n\t"
+        "addc.u32 t20, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t41, %20, %21, t41;\n\t"
         "madc.hi.cc.u32 t42, %20, %21, t42;\n\t"
         "madc.lo.cc.u32 t43, %20, %23, t43;\n\t"
@@ -1260,61 +1233,54 @@ struct F_X448 {
         "madc.lo.cc.u32 t45, %20, %25, t45;\n\t"
         "madc.hi.cc.u32 t46, %20, %25, t46;\n\t"
         "madc.lo.cc.u32 t47, %20, %27, t47;\n\t"
-        "madc.hi.cc.u32 t48, %20, %27, 0x0;\n\t"
-        "addc.u32 t49, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t48, %20, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t16, %21, %23, t16;\n\t"
         "madc.hi.cc.u32 t17, %21, %23, t17;\n\t"
         "madc.lo.cc.u32 t18, %21, %25, t18;\n\t"
         "madc.hi.cc.u32 t19, %21, %25, t19;\n\t"
         "madc.lo.cc.u32 t20, %21, %27, t20;\n\t"
-        "madc.hi.cc.u32 t21, %21, %27, 0x0;\n\t"
-        "addc.u32 t22, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t21, %21, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t43, %21, %22, t43;\n\t"
         "madc.hi.cc.u32 t44, %21, %22, t44;\n\t"
         "madc.lo.cc.u32 t45, %21, %24, t45;\n\t"
         "madc.hi.cc.u32 t46, %21, %24, t46;\n\t"
         "madc.lo.cc.u32 t47, %21, %26, t47;\n\t"
         "madc.hi.cc.u32 t48, %21, %26, t48;\n\t"
-        "addc.u32 t49, t49, 0x0;\n\t"
+        "addc.u32 t49, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t18, %22, %24, t18;\n\t"
         "madc.hi.cc.u32 t19, %22, %24, t19;\n\t"
         "madc.lo.cc.u32 t20, %22, %26, t20;\n\t"
         "madc.hi.cc.u32 t21, %22, %26, t21;\n\t"
-        "addc.u32 t22, t22, 0x0;\n\t"
+        "addc.u32 t22, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t45, %22, %23, t45;\n\t"
         "madc.hi.cc.u32 t46, %22, %23, t46;\n\t"
         "madc.lo.cc.u32 t47, %22, %25, t47;\n\t"
         "madc.hi.cc.u32 t48, %22, %25, t48;\n\t"
         "madc.lo.cc.u32 t49, %22, %27, t49;\n\t"
-        "madc.hi.cc.u32 t50, %22, %27, 0x0;\n\t"
-        "addc.u32 t51, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t50, %22, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t20, %23, %25, t20;\n\t"
         "madc.hi.cc.u32 t21, %23, %25, t21;\n\t"
         "madc.lo.cc.u32 t22, %23, %27, t22;\n\t"
-        "madc.hi.cc.u32 t23, %23, %27, 0x0;\n\t"
-        "addc.u32 t24, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t23, %23, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t47, %23, %24, t47;\n\t"
         "madc.hi.cc.u32 t48, %23, %24, t48;\n\t"
         "madc.lo.cc.u32 t49, %23, %26, t49;\n\t"
         "madc.hi.cc.u32 t50, %23, %26, t50;\n\t"
-        "addc.u32 t51, t51, 0x0;\n\t"
+        "addc.u32 t51, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t22, %24, %26, t22;\n\t"
         "madc.hi.cc.u32 t23, %24, %26, t23;\n\t"
-        "addc.u32 t24, t24, 0x0;\n\t"
+        "addc.u32 t24, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t49, %24, %25, t49;\n\t"
         "madc.hi.cc.u32 t50, %24, %25, t50;\n\t"
         "madc.lo.cc.u32 t51, %24, %27, t51;\n\t"
-        "madc.hi.cc.u32 t52, %24, %27, 0x0;\n\t"
-        "addc.u32 t53, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t52, %24, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t24, %25, %27, t24;\n\t"
-        "madc.hi.cc.u32 t25, %25, %27, 0x0;\n\t"
-        "addc.u32 t26, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t25, %25, %27, 0x0;\n\t"
         "mad.lo.cc.u32 t51, %25, %26, t51;\n\t"
         "madc.hi.cc.u32 t52, %25, %26, t52;\n\t"
-        "addc.u32 t53, t53, 0x0;\n\t"
+        "addc.u32 t53, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t53, %26, %27, t53;\n\t"
-        "madc.hi.cc.u32 t54, %26, %27, 0x0;\n\t"
-        "addc.u32 t55, 0x0, 0x0;\n\t"
+        "madc.hi.u32 t54, %26, %27, 0x0;\n\t"
         "add.cc.u32 t56, t2, t30;\n\t"
         "addc.cc.u32 t57, t3, t31;\n\t"
         "addc.cc.u32 t58, t4, t32;\n\t"
@@ -1339,8 +1305,8 @@ struct F_X448 {
         "addc.cc.u32 t77, t23, t51;\n\t"
         "addc.cc.u32 t78, t24, t52;\n\t"
         "addc.cc.u32 t79, t25, t53;\n\t"
-        "addc.cc.u32 t80, t26, t54;\n\t"
-        "addc.u32 t81, 0x0, t55;\n\t"
+        "addc.cc.u32 t80, 0x0, t54;\n\t"
+        "addc.u32 t81, 0x0, 0x0;\n\t"
         "shl.b32 t82, t29, 1;\n\t"
         "shf.l.wrap.b32 t83, t29, t56, 1;\n\t"
         "shf.l.wrap.b32 t84, t56, t57, 1;\n\t"
@@ -1528,8 +1494,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_1_i * a_11_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * a_11_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_1_i * a_13_i) + 0x0u + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_1_i * a_13_i) >> 32) + 0x0u + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t16 = (uint32_t)w_;
+    w_ = (((uint64_t)a_1_i * a_13_i) >> 32) + 0x0u + cf_; t15 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_1_i * a_2_i) + t31; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_1_i * a_2_i) >> 32) + t32 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_1_i * a_4_i) + t33 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1553,7 +1518,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_2_i * a_10_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_12_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_12_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t16 + 0x0u + cf_; t16 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t16 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_2_i * a_3_i) + t33; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_3_i) >> 32) + t34 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_5_i) + t35 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1565,8 +1530,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_2_i * a_11_i) + t41 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_2_i * a_11_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_2_i * a_13_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_2_i * a_13_i) >> 32) + 0x0u + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t45 = (uint32_t)w_;
+    w_ = (((uint64_t)a_2_i * a_13_i) >> 32) + 0x0u + cf_; t44 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_3_i * a_5_i) + t8; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_5_i) >> 32) + t9 + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_7_i) + t10 + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1576,8 +1540,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_3_i * a_11_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_11_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_13_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_3_i * a_13_i) >> 32) + 0x0u + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t18 = (uint32_t)w_;
+    w_ = (((uint64_t)a_3_i * a_13_i) >> 32) + 0x0u + cf_; t17 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_3_i * a_4_i) + t35; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_4_i) >> 32) + t36 + cf_; t36 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_6_i) + t37 + cf_; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1588,7 +1551,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_3_i * a_10_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_3_i * a_12_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_3_i * a_12_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t45 + 0x0u + cf_; t45 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t45 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_4_i * a_6_i) + t10; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_6_i) >> 32) + t11 + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_4_i * a_8_i) + t12 + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1597,7 +1560,7 @@ struct F_X448 {
     w_ = (((uint64_t)a_4_i * a_10_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_4_i * a_12_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_12_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t18 + 0x0u + cf_; t18 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t18 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_4_i * a_5_i) + t37; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_5_i) >> 32) + t38 + cf_; t38 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_4_i * a_7_i) + t39 + cf_; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1607,8 +1570,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_4_i * a_11_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_4_i * a_11_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_4_i * a_13_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_4_i * a_13_i) >> 32) + 0x0u + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t47 = (uint32_t)w_;
+    w_ = (((uint64_t)a_4_i * a_13_i) >> 32) + 0x0u + cf_; t46 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_5_i * a_7_i) + t12; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * a_7_i) >> 32) + t13 + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_5_i * a_9_i) + t14 + cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1616,8 +1578,7 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_5_i * a_11_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * a_11_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_5_i * a_13_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_5_i * a_13_i) >> 32) + 0x0u + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t20 = (uint32_t)w_;
+    w_ = (((uint64_t)a_5_i * a_13_i) >> 32) + 0x0u + cf_; t19 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_5_i * a_6_i) + t39; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * a_6_i) >> 32) + t40 + cf_; t40 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_5_i * a_8_i) + t41 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1626,14 +1587,14 @@ struct F_X448 {
     w_ = (((uint64_t)a_5_i * a_10_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_5_i * a_12_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_5_i * a_12_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t47 + 0x0u + cf_; t47 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t47 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_6_i * a_8_i) + t14; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * a_8_i) >> 32) + t15 + cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * a_10_i) + t16 + cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * a_10_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * a_12_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * a_12_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t20 + 0x0u + cf_; t20 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t20 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_6_i * a_7_i) + t41; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * a_7_i) >> 32) + t42 + cf_; t42 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * a_9_i) + t43 + cf_; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1641,61 +1602,54 @@ struct F_X448 {
     w_ = (uint64_t)(uint32_t)(a_6_i * a_11_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * a_11_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * a_13_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_6_i * a_13_i) >> 32) + 0x0u + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t49 = (uint32_t)w_;
+    w_ = (((uint64_t)a_6_i * a_13_i) >> 32) + 0x0u + cf_; t48 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_7_i * a_9_i) + t16; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_7_i * a_9_i) >> 32) + t17 + cf_; t17 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * a_11_i) + t18 + cf_; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_7_i * a_11_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * a_13_i) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_7_i * a_13_i) >> 32) + 0x0u + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t22 = (uint32_t)w_;
+    w_ = (((uint64_t)a_7_i * a_13_i) >> 32) + 0x0u + cf_; t21 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_7_i * a_8_i) + t43; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_7_i * a_8_i) >> 32) + t44 + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * a_10_i) + t45 + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_7_i * a_10_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_7_i * a_12_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_7_i * a_12_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t49 + 0x0u + cf_; t49 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t49 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_8_i * a_10_i) + t18; t18 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_8_i * a_10_i) >> 32) + t19 + cf_; t19 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_8_i * a_12_i) + t20 + cf_; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_8_i * a_12_i) >> 32) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t22 + 0x0u + cf_; t22 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t22 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_8_i * a_9_i) + t45; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_8_i * a_9_i) >> 32) + t46 + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_8_i * a_11_i) + t47 + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_8_i * a_11_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_8_i * a_13_i) + t49 + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_8_i * a_13_i) >> 32) + 0x0u + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t51 = (uint32_t)w_;
+    w_ = (((uint64_t)a_8_i * a_13_i) >> 32) + 0x0u + cf_; t50 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_9_i * a_11_i) + t20; t20 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_9_i * a_11_i) >> 32) + t21 + cf_; t21 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_9_i * a_13_i) + t22 + cf_; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_9_i * a_13_i) >> 32) + 0x0u + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t24 = (uint32_t)w_;
+    w_ = (((uint64_t)a_9_i * a_13_i) >> 32) + 0x0u + cf_; t23 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_9_i * a_10_i) + t47; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_9_i * a_10_i) >> 32) + t48 + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_9_i * a_12_i) + t49 + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_9_i * a_12_i) >> 32) + t50 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t51 + 0x0u + cf_; t51 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t51 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_10_i * a_12_i) + t22; t22 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_10_i * a_12_i) >> 32) + t23 + cf_; t23 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t24 + 0x0u + cf_; t24 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t24 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_10_i * a_11_i) + t49; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_10_i * a_11_i) >> 32) + t50 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_10_i * a_13_i) + t51 + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_10_i * a_13_i) >> 32) + 0x0u + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t53 = (uint32_t)w_;
+    w_ = (((uint64_t)a_10_i * a_13_i) >> 32) + 0x0u + cf_; t52 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_11_i * a_13_i) + t24; t24 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_11_i * a_13_i) >> 32) + 0x0u + cf_; t25 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t26 = (uint32_t)w_;
+    w_ = (((uint64_t)a_11_i * a_13_i) >> 32) + 0x0u + cf_; t25 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_11_i * a_12_i) + t51; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_11_i * a_12_i) >> 32) + t52 + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t53 + 0x0u + cf_; t53 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t53 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_12_i * a_13_i) + t53; t53 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_12_i * a_13_i) >> 32) + 0x0u + cf_; t54 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t55 = (uint32_t)w_;
+    w_ = (((uint64_t)a_12_i * a_13_i) >> 32) + 0x0u + cf_; t54 = (uint32_t)w_;
     w_ = (uint64_t)t2 + t30; t56 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t31 + cf_; t57 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t4 + t32 + cf_; t58 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1720,8 +1674,8 @@ struct F_X448 {
     w_ = (uint64_t)t23 + t51 + cf_; t77 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t24 + t52 + cf_; t78 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t25 + t53 + cf_; t79 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t26 + t54 + cf_; t80 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + t55 + cf_; t81 = (uint32_t)w_;
+    w_ = (uint64_t)0x0u + t54 + cf_; t80 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t81 = (uint32_t)w_;
     t82 = (uint32_t)(t29 << 1);
     t83 = (uint32_t)(((((uint64_t)t56 << 32) | t29) << 1) >> 32);
     t84 = (uint32_t)(((((uint64_t)t57 << 32) | t56) << 1) >> 32);
@@ -2041,6 +1995,211 @@ struct F_X448 {
     r[11] = t53;
     r[12] = t54;
     r[13] = t55;
+#endif
+  }
+
+  // r = a*b + c, small integer b: modmli + modadd fused (rfc7748.c:209,212)
+  static MAB_DEV void mla(uint32_t (&r)[14], const uint32_t (&a)[14], uint32_t b, const uint32_t (&c)[14]) {
+#ifndef MAB_HOSTSIM
+    asm("{\n\t"
+        ".reg .u32 t<67>;\n\t"
+        "mad.lo.cc.u32 t0, %14, %42, %28;\n\t"
+        "madc.hi.cc.u32 t1, %14, %42, %29;\n\t"
+        "madc.lo.cc.u32 t2, %16, %42, %30;\n\t"
+        "madc.hi.cc.u32 t3, %16, %42, %31;\n\t"
+        "madc.lo.cc.u32 t4, %18, %42, %32;\n\t"
+        "madc.hi.cc.u32 t5, %18, %42, %33;\n\t"
+        "madc.lo.cc.u32 t6, %20, %42, %34;\n\t"
+        "madc.hi.cc.u32 t7, %20, %42, %35;\n\t"
+        "madc.lo.cc.u32 t8, %22, %42, %36;\n\t"
+        "madc.hi.cc.u32 t9, %22, %42, %37;\n\t"
+        "madc.lo.cc.u32 t10, %24, %42, %38;\n\t"
+        "madc.hi.cc.u32 t11, %24, %42, %39;\n\t"
+        "madc.lo.cc.u32 t12, %26, %42, %40;\n\t"
+        "madc.hi.cc.u32 t13, %26, %42, %41;\n\t"
+        "addc.u32 t14, 0x0, 0x0;\n\t"
+        "mul.lo.u32 t15, %15, %42;\n\t"
+        "mul.hi.u32 t16, %15, %42;\n\t"
+        "mul.lo.u32 t17, %17, %42;\n\t"
+        "mul.hi.u32 t18, %17, %42;\n\t"
+        "mul.lo.u32 t19, %19, %42;\n\t"
+        "mul.hi.u32 t20, %19, %42;\n\t"
+        "mul.lo.u32 t21, %21, %42;\n\t"
+        "mul.hi.u32 t22, %21, %42;\n\t"
+        "mul.lo.u32 t23, %23, %42;\n\t"
+        "mul.hi.u32 t24, %23, %42;\n\t"
+        "mul.lo.u32 t25, %25, %42;\n\t"
+        "mul.hi.u32 t26, %25, %42;\n\t"
+        "mul.lo.u32 t27, %27, %42;\n\t"
+        "mul.hi.u32 t28, %27, %42;\n\t"
+        "add.cc.u32 t29, t1, t15;\n\t"
+        "addc.cc.u32 t30, t2, t16;\n\t"
+        "addc.cc.u32 t31, t3, t17;\n\t"
+        "addc.cc.u32 t32, t4, t18;\n\t"
+        "addc.cc.u32 t33, t5, t19;\n\t"
+        "addc.cc.u32 t34, t6, t20;\n\t"
+        "addc.cc.u32 t35, t7, t21;\n\t"
+        "addc.cc.u32 t36, t8, t22;\n\t"
+        "addc.cc.u32 t37, t9, t23;\n\t"
+        "addc.cc.u32 t38, t10, t24;\n\t"
+        "addc.cc.u32 t39, t11, t25;\n\t"
+        "addc.cc.u32 t40, t12, t26;\n\t"
+        "addc.cc.u32 t41, t13, t27;\n\t"
+        "addc.u32 t42, t14, t28;\n\t"
+        "add.cc.u32 t43, t0, t42;\n\t"
+        "addc.cc.u32 t44, t29, 0x0;\n\t"
+        "addc.cc.u32 t45, t30, 0x0;\n\t"
+        "addc.cc.u32 t46, t31, 0x0;\n\t"
+        "addc.cc.u32 t47, t32, 0x0;\n\t"
+        "addc.cc.u32 t48, t33, 0x0;\n\t"
+        "addc.cc.u32 t49, t34, 0x0;\n\t"
+        "addc.cc.u32 t50, t35, t42;\n\t"
+        "addc.cc.u32 t51, t36, 0x0;\n\t"
+        "addc.cc.u32 t52, t37, 0x0;\n\t"
+        "addc.cc.u32 t53, t38, 0x0;\n\t"
+        "addc.cc.u32 t54, t39, 0x0;\n\t"
+        "addc.cc.u32 t55, t40, 0x0;\n\t"
+        "addc.cc.u32 t56, t41, 0x0;\n\t"
+        "addc.u32 t57, 0x0, 0x0;\n\t"
+        "add.cc.u32 t58, t43, t57;\n\t"
+        "addc.cc.u32 t59, t44, 0x0;\n\t"
+        "addc.cc.u32 t60, t45, 0x0;\n\t"
+        "addc.cc.u32 t61, t46, 0x0;\n\t"
+        "addc.cc.u32 t62, t47, 0x0;\n\t"
+        "addc.cc.u32 t63, t48, 0x0;\n\t"
+        "addc.cc.u32 t64, t49, 0x0;\n\t"
+        "addc.cc.u32 t65, t50, t57;\n\t"
+        "addc.u32 t66, t51, 0x0;\n\t"
+        "mov.u32 %0, t58;\n\t"
+        "mov.u32 %1, t59;\n\t"
+        "mov.u32 %2, t60;\n\t"
+        "mov.u32 %3, t61;\n\t"
+        "mov.u32 %4, t62;\n\t"
+        "mov.u32 %5, t63;\n\t"
+        "mov.u32 %6, t64;\n\t"
+        "mov.u32 %7, t65;\n\t"
+        "mov.u32 %8, t66;\n\t"
+        "mov.u32 %9, t52;\n\t"
+        "mov.u32 %10, t53;\n\t"
+        "mov.u32 %11, t54;\n\t"
+        "mov.u32 %12, t55;\n\t"
+        "mov.u32 %13, t56;\n\t"
+        "}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]), "r"(c[9]), "r"(c[10]), "r"(c[11]), "r"(c[12]), "r"(c[13]), "r"(b));
+#else
+    const uint32_t a_0_i = a[0];
+    const uint32_t a_1_i = a[1];
+    const uint32_t a_2_i = a[2];
+    const uint32_t a_3_i = a[3];
+    const uint32_t a_4_i = a[4];
+    const uint32_t a_5_i = a[5];
+    const uint32_t a_6_i = a[6];
+    const uint32_t a_7_i = a[7];
+    const uint32_t a_8_i = a[8];
+    const uint32_t a_9_i = a[9];
+    const uint32_t a_10_i = a[10];
+    const uint32_t a_11_i = a[11];
+    const uint32_t a_12_i = a[12];
+    const uint32_t a_13_i = a[13];
+    const uint32_t c_0_i = c[0];
+    const uint32_t c_1_i = c[1];
+    const uint32_t c_2_i = c[2];
+    const uint32_t c_3_i = c[3];
+    const uint32_t c_4_i = c[4];
+    const uint32_t c_5_i = c[5];
+    const uint32_t c_6_i = c[6];
+    const uint32_t c_7_i = c[7];
+    const uint32_t c_8_i = c[8];
+    const uint32_t c_9_i = c[9];
+    const uint32_t c_10_i = c[10];
+    const uint32_t c_11_i = c[11];
+    const uint32_t c_12_i = c[12];
+    const uint32_t c_13_i = c[13];
+    const uint32_t b_i = b;
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18, t19, t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31, t32, t33, t34, t35, t36, t37, t38, t39, t40, t41, t42, t43, t44, t45, t46, t47, t48, t49, t50, t51, t52, t53, t54, t55, t56, t57, t58, t59, t60, t61, t62, t63, t64, t65, t66;
+    uint64_t w_; uint32_t cf_ = 0; (void)cf_; (void)w_;
+    w_ = (uint64_t)(uint32_t)(a_0_i * b_i) + c_0_i; t0 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_0_i * b_i) >> 32) + c_1_i + cf_; t1 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_2_i * b_i) + c_2_i + cf_; t2 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_2_i * b_i) >> 32) + c_3_i + cf_; t3 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_4_i * b_i) + c_4_i + cf_; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_4_i * b_i) >> 32) + c_5_i + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_6_i * b_i) + c_6_i + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_6_i * b_i) >> 32) + c_7_i + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_8_i * b_i) + c_8_i + cf_; t8 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_8_i * b_i) >> 32) + c_9_i + cf_; t9 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_10_i * b_i) + c_10_i + cf_; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_10_i * b_i) >> 32) + c_11_i + cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)(uint32_t)(a_12_i * b_i) + c_12_i + cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_12_i * b_i) >> 32) + c_13_i + cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t14 = (uint32_t)w_;
+    t15 = (uint32_t)((uint32_t)(a_1_i * b_i));
+    t16 = (uint32_t)(((uint64_t)a_1_i * b_i) >> 32);
+    t17 = (uint32_t)((uint32_t)(a_3_i * b_i));
+    t18 = (uint32_t)(((uint64_t)a_3_i * b_i) >> 32);
+    t19 = (uint32_t)((uint32_t)(a_5_i * b_i));
+    t20 = (uint32_t)(((uint64_t)a_5_i * b_i) >> 32);
+    t21 = (uint32_t)((uint32_t)(a_7_i * b_i));
+    t22 = (uint32_t)(((uint64_t)a_7_i * b_i) >> 32);
+    t23 = (uint32_t)((uint32_t)(a_9_i * b_i));
+    t24 = (uint32_t)(((uint64_t)a_9_i * b_i) >> 32);
+    t25 = (uint32_t)((uint32_t)(a_11_i * b_i));
+    t26 = (uint32_t)(((uint64_t)a_11_i * b_i) >> 32);
+    t27 = (uint32_t)((uint32_t)(a_13_i * b_i));
+    t28 = (uint32_t)(((uint64_t)a_13_i * b_i) >> 32);
+    w_ = (uint64_t)t1 + t15; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t2 + t16 + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t3 + t17 + cf_; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t4 + t18 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t5 + t19 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t6 + t20 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t7 + t21 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t8 + t22 + cf_; t36 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t9 + t23 + cf_; t37 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t10 + t24 + cf_; t38 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t11 + t25 + cf_; t39 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t12 + t26 + cf_; t40 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t13 + t27 + cf_; t41 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t14 + t28 + cf_; t42 = (uint32_t)w_;
+    w_ = (uint64_t)t0 + t42; t43 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t29 + 0x0u + cf_; t44 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t30 + 0x0u + cf_; t45 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t31 + 0x0u + cf_; t46 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t32 + 0x0u + cf_; t47 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t33 + 0x0u + cf_; t48 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t34 + 0x0u + cf_; t49 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t35 + t42 + cf_; t50 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t36 + 0x0u + cf_; t51 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t37 + 0x0u + cf_; t52 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t38 + 0x0u + cf_; t53 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t39 + 0x0u + cf_; t54 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t40 + 0x0u + cf_; t55 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t41 + 0x0u + cf_; t56 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t57 = (uint32_t)w_;
+    w_ = (uint64_t)t43 + t57; t58 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t44 + 0x0u + cf_; t59 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t45 + 0x0u + cf_; t60 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t46 + 0x0u + cf_; t61 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t47 + 0x0u + cf_; t62 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t48 + 0x0u + cf_; t63 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t49 + 0x0u + cf_; t64 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t50 + t57 + cf_; t65 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t51 + 0x0u + cf_; t66 = (uint32_t)w_;
+    r[0] = t58;
+    r[1] = t59;
+    r[2] = t60;
+    r[3] = t61;
+    r[4] = t62;
+    r[5] = t63;
+    r[6] = t64;
+    r[7] = t65;
+    r[8] = t66;
+    r[9] = t52;
+    r[10] = t53;
+    r[11] = t54;
+    r[12] = t55;
+    r[13] = t56;
 #endif
   }
 

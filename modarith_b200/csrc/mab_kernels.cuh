@@ -13,7 +13,7 @@
 enum MabOp {
   OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_SQR, OP_MLI, OP_CPY, OP_NSQR, OP_PRO, OP_INV, OP_INVH,
   OP_QR, OP_QRH, OP_SQRT, OP_SQRTH, OP_IS1, OP_IS0, OP_ZER, OP_ONE, OP_INT, OP_NRES, OP_REDC,
-  OP_CSW, OP_CMV, OP_SHL, OP_SHR, OP_HAF, OP_2R, OP_SIGN, OP_CMP, OP_FSB
+  OP_CSW, OP_CMV, OP_SHL, OP_SHR, OP_HAF, OP_2R, OP_SIGN, OP_CMP, OP_FSB, OP_MULCHAIN
 };
 
 struct MabArgs {
@@ -42,7 +42,7 @@ template <class F, int OP> __global__ void __launch_bounds__(128) k_field(MabArg
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   uint32_t a[L], b[L], r[L];
-  if constexpr (OP == OP_ADD || OP == OP_SUB || OP == OP_MUL || OP == OP_CMP || OP == OP_INVH ||
+  if constexpr (OP == OP_ADD || OP == OP_SUB || OP == OP_MUL || OP == OP_CMP || OP == OP_INVH || OP == OP_MULCHAIN ||
                 OP == OP_SQRTH || OP == OP_QRH) {
     plane_ld<L>(a, p.a, p.stride, i);
     plane_ld<L>(b, p.b, p.stride, i);
@@ -58,6 +58,11 @@ template <class F, int OP> __global__ void __launch_bounds__(128) k_field(MabArg
   if constexpr (OP == OP_NEG) F::neg(r, a);
   if constexpr (OP == OP_MUL) F::mul(r, a, b);
   if constexpr (OP == OP_SQR) F::sqr(r, a);
+  if constexpr (OP == OP_MULCHAIN) {        // measurement helper: r = a * b^scalar, register resident
+    Fd::cpy(r, a);
+    MAB_NOUNROLL
+    for (uint32_t it = 0; it < p.scalar; it++) F::mul(r, r, b);
+  }
   if constexpr (OP == OP_MLI) F::mli(r, a, p.scalar);
   if constexpr (OP == OP_CPY) Fd::cpy(r, a);
   if constexpr (OP == OP_NSQR) { Fd::cpy(r, a); Fd::nsqr(r, (int)p.scalar); }
@@ -171,7 +176,14 @@ template <class F> __global__ void __launch_bounds__(128) k_exp(const uint32_t* 
 #ifndef MAB_LADDER_THREADS
 #define MAB_LADDER_THREADS 128
 #endif
-template <class F> __global__ void __launch_bounds__(MAB_LADDER_THREADS) k_rfc7748(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
+// resident CTAs per SM the ladder is compiled for: chosen per modulus by the generator
+// (F::LADDER_MINBLOCKS: 4 for X25519 = 110 registers, no spills) unless overridden for experiments
+#ifdef MAB_LADDER_MINBLOCKS
+#define MAB_LADDER_BOUNDS(F) __launch_bounds__(MAB_LADDER_THREADS, MAB_LADDER_MINBLOCKS)
+#else
+#define MAB_LADDER_BOUNDS(F) __launch_bounds__(MAB_LADDER_THREADS, F::LADDER_MINBLOCKS)
+#endif
+template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
   constexpr int L = F::L;
   static_assert(F::NBYTES == 4 * L, "byte strings are whole words for the supported curves");
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -5,10 +5,13 @@
 #include <cuda_runtime.h>
 #include <string.h>
 #include <stdio.h>
-#include "../../include/modarith_b200.h"
+#include "modarith_b200.h"
 #include "gen/field_X25519.cuh"
 #include "gen/field_X448.cuh"
 #include "gen/field_NIST256.cuh"
+#include "mab_probe.cuh"
+#include "mab_workspace.h"
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------
 // Each thread runs NCH independent accumulator chains so the 4-5 cycle IMAD latency never
@@ -74,6 +77,47 @@ template <int VARIANT> __global__ void __launch_bounds__(256) k_imad_peak(const 
   if (acc == 0x12345678u) sink[0] = acc;        // practically never: keeps the chains live
 }
 
+template <int V> static void launch_probe(int v, int blocks, int threads, cudaStream_t st, const uint32_t* d, uint32_t* sink, int iters) {
+  if (v == V) k_probe<V><<<blocks, threads, 0, st>>>(d, sink, iters);
+  if constexpr (V + 1 < MAB_NPROBE) launch_probe<V + 1>(v, blocks, threads, st, d, sink, iters);
+}
+
+// ---- host-path workspace cache: one per device, guarded by a mutex held for the whole call ----
+static MabWorkspace g_ws[MAB_WS_MAXDEV];
+static std::mutex g_ws_mutex[MAB_WS_MAXDEV];
+
+int mab_host_workspace_acquire(int device, size_t bytes, MabWorkspace** out) {
+  if (device < 0 || device >= MAB_WS_MAXDEV) return MAB_ERR_BADARG;
+  g_ws_mutex[device].lock();
+  MabWorkspace* ws = &g_ws[device];
+  cudaError_t e = cudaSuccess;
+  if (!ws->ready) {
+    for (int s = 0; s < MAB_WS_STREAMS && e == cudaSuccess; s++) {
+      ws->buf[s] = nullptr;
+      e = cudaStreamCreateWithFlags(&ws->stream[s], cudaStreamNonBlocking);
+    }
+    ws->bytes = 0;
+    ws->device = device;
+    ws->ready = (e == cudaSuccess);
+  }
+  if (e == cudaSuccess && ws->bytes < bytes) {
+    for (int s = 0; s < MAB_WS_STREAMS && e == cudaSuccess; s++) {
+      if (ws->buf[s]) cudaFree(ws->buf[s]);
+      ws->buf[s] = nullptr;
+      e = cudaMalloc((void**)&ws->buf[s], bytes);
+    }
+    ws->bytes = (e == cudaSuccess) ? bytes : 0;
+  }
+  if (e != cudaSuccess) {
+    g_ws_mutex[device].unlock();
+    return (int)e;
+  }
+  *out = ws;
+  return 0;
+}
+
+void mab_host_workspace_release(MabWorkspace* ws) { g_ws_mutex[ws->device].unlock(); }
+
 static const char* kVersion = "modarith_b200 0.1 (sm_100a)";
 
 // W(modmul)=L^2, W(modsqr)=L(L+1)/2, W(modmli)=L with L=ceil(Nbits/32); chains
@@ -109,6 +153,25 @@ const char* mab_error_string(int code) {
   if (code == MAB_ERR_BADARG) return "modarith_b200: bad argument";
   if (code == MAB_ERR_NODEVICE) return "modarith_b200: no CUDA device";
   return cudaGetErrorString((cudaError_t)code);
+}
+
+void mab_release_workspaces(void) {
+  for (int d = 0; d < MAB_WS_MAXDEV; d++) {
+    std::lock_guard<std::mutex> g(g_ws_mutex[d]);
+    MabWorkspace* ws = &g_ws[d];
+    if (!ws->ready) continue;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(d);
+    for (int s = 0; s < MAB_WS_STREAMS; s++) {
+      if (ws->buf[s]) cudaFree(ws->buf[s]);
+      cudaStreamDestroy(ws->stream[s]);
+      ws->buf[s] = nullptr;
+    }
+    ws->bytes = 0;
+    ws->ready = false;
+    cudaSetDevice(prev);
+  }
 }
 
 int mab_device_count(void) {
@@ -172,6 +235,38 @@ int mab_imad_peak(int variant, int iters, int blocks, int threads, float* ms, do
   // 4 x 2*NCH 32-bit MADs (variants 1,2), 4 x 2*NCH adds (variant 6)
   double per_iter = (variant == 1 || variant == 2 || variant >= 6) ? 4.0 * 2 * NCH : 4.0 * NCH;
   if (instructions) *instructions = per_iter * (double)iters * (double)blocks * (double)threads;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d);
+  return (int)e;
+}
+
+int mab_pipe_probe(int variant, int iters, int blocks, int threads, float* ms, const char** name, int* nwide, int* nalu, void* stream) {
+  if (variant < 0 || variant >= MAB_NPROBE) return MAB_ERR_BADARG;
+  if (iters <= 0 || blocks <= 0 || threads <= 0 || threads > 256) return MAB_ERR_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t host[64];
+  for (int i = 0; i < 64; i++) host[i] = 0x9e3779b9u * (i + 1) | 1u;
+  uint32_t* d = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d, 65 * sizeof(uint32_t));
+  if (e != cudaSuccess) return (int)e;
+  cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice);
+  cudaEvent_t t0, t1;
+  cudaEventCreate(&t0);
+  cudaEventCreate(&t1);
+  for (int rep = 0; rep < 2; rep++) {
+    cudaEventRecord(t0, st);
+    launch_probe<0>(variant, blocks, threads, st, d, d + 64, iters);
+    cudaEventRecord(t1, st);
+    cudaEventSynchronize(t1);
+  }
+  e = cudaGetLastError();
+  float t = 0.f;
+  cudaEventElapsedTime(&t, t0, t1);
+  if (ms) *ms = t;
+  if (name) *name = kProbeNames[variant];
+  if (nwide) *nwide = 0;
+  if (nalu) *nalu = 0;
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   cudaFree(d);

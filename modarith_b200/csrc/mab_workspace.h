@@ -1,0 +1,16 @@
+// mab_workspace.h -- per-device staging area of the host-pointer entry points (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#define MAB_WS_STREAMS 3
+#define MAB_WS_MAXDEV 64
+struct MabWorkspace {
+  cudaStream_t stream[MAB_WS_STREAMS];
+  char* buf[MAB_WS_STREAMS];
+  size_t bytes;          // capacity of each buf
+  int device;
+  bool ready;
+};
+// Locks the device's workspace, growing each of its three buffers to at least `bytes`.
+int mab_host_workspace_acquire(int device, size_t bytes, MabWorkspace** out);
+void mab_host_workspace_release(MabWorkspace* ws);

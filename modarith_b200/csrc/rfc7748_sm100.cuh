@@ -36,21 +36,21 @@ template <class F> struct Rfc7748 {
     Fd::cpy(x3, x1);
     Fd::one(z3);
 
-    // align bit Nbits-1 of the scalar with bit 31 of the top word
-    constexpr int lead = 32 * L - F::NBITS;
-    if (lead > 0) {
-#pragma unroll
-      for (int j = L - 1; j > 0; j--) k[j] = mab_shf_l(k[j - 1], k[j], lead);
-      k[0] <<= lead;
-    }
+    // The scalar is consumed from the top: the current word sits in k[L-1] and is shifted left one
+    // bit per step; after its last bit the words rotate up by one.  Two ALU instructions per step and
+    // no dynamically indexed register (bit(), rfc7748.c:144-146, indexes a byte array instead).
+    constexpr int topbits = F::NBITS - 32 * (L - 1);        // bits of the scalar held by the top word
+    if (topbits < 32) k[L - 1] <<= (32 - topbits);
 
     uint32_t swap = 0;
     MAB_NOUNROLL
-    for (int i = F::NBITS - 1; i >= 0; i--) {    // rfc7748.c:186-221
-      uint32_t kt = k[L - 1] >> 31;
-#pragma unroll
-      for (int j = L - 1; j > 0; j--) k[j] = mab_shf_l(k[j - 1], k[j], 1);
-      k[0] <<= 1;
+    for (int w = L - 1; w >= 0; w--) {           // rfc7748.c:186-221, bits Nbits-1 .. 0
+      uint32_t kw = k[L - 1];
+      const int nb = (w == L - 1) ? topbits : 32;
+      MAB_NOUNROLL
+      for (int bi = 0; bi < nb; bi++) {
+      uint32_t kt = kw >> 31;
+      kw <<= 1;
       swap ^= kt;
       Fd::csw(swap, x2, x3);
       Fd::csw(swap, z2, z3);
@@ -72,9 +72,11 @@ template <class F> struct Rfc7748 {
       F::mul(z3, z3, x1);                        // z3 = x1*(DA-CB)^2
       F::mul(x2, A, B);                          // x2 = AA*BB
       F::sub(B, A, B);                           // E = AA-BB
-      F::mli(z2, B, F::A24);                     // a24*E
-      F::add(z2, z2, A);
+      F::mla(z2, B, F::A24, A);                  // a24*E + AA  (modmli + modadd fused)
       F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
+      }
+#pragma unroll
+      for (int j = L - 1; j > 0; j--) k[j] = k[j - 1];
     }
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);

@@ -87,6 +87,10 @@ class Field:
     def modsqr(self, a, c):
         self._call("modsqr", [_ptr(a), _ptr(c)], self._chk(a, c))
 
+    def bench_modmul(self, a, b, c, iters: int):
+        """measurement helper: c = a * b^iters with the running product in registers"""
+        self._call("bench_modmul", [_ptr(a), _ptr(b), _ptr(c), int(iters)], self._chk(a, b, c))
+
     def modmli(self, a, b: int, c):
         self._call("modmli", [_ptr(a), int(b), _ptr(c)], self._chk(a, c))
 

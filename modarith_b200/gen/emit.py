@@ -55,7 +55,7 @@ def emit_field_header(plan: Plan) -> str:
     out.append("// plan %s: %d saturated 32-bit limbs; stored values < %s; R = 2^%d\n" % (
         type(plan).__name__, L, "p" if plan.bound == P.p else "2^%d" % (32 * L),
         plan.R.bit_length() - 1))
-    for k in ("mul", "sqr", "mli", "add", "sub", "canon"):
+    for k in ("mul", "sqr", "mli", "mla", "add", "sub", "canon"):
         w, i, a = blocks[k].stats()
         out.append("//   %-5s : %3d IMAD.WIDE  %2d IMAD  ~%3d ALU-pipe ops\n" % (k, w, i, a))
     out.append("//   modpro: %d squarings + %d multiplies (exponent (p-1-2^k)/2^(k+1), k=%d)\n" %
@@ -68,6 +68,8 @@ def emit_field_header(plan: Plan) -> str:
     out.append("  static constexpr int PM1D2 = %d;\n" % P.pm1d2)
     out.append("  static constexpr bool MONTGOMERY = %s;\n" % ("true" if plan.R != 1 else "false"))
     out.append("  static constexpr int PRO_SQR = %d, PRO_MUL = %d;\n" % (nsq, nmu))
+    out.append("  static constexpr int LADDER_MINBLOCKS = %d;   // resident 128-thread CTAs per SM for k_rfc7748\n"
+               % plan.ladder_minblocks)
     if P.a24 is not None:
         out.append("  static constexpr bool HAS_CURVE = true;\n")
         out.append("  static constexpr uint32_t A24 = %d;\n" % P.a24)
@@ -86,6 +88,8 @@ def emit_field_header(plan: Plan) -> str:
     out.append(_block_fn(plan, "sqr", blocks["sqr"], "%s, %s" % (r, a)))
     out.append("  // c = a*b for a small integer b (pseudo.py:705-728 / monty.py:876-978)\n")
     out.append(_block_fn(plan, "mli", blocks["mli"], "%s, %s, uint32_t b" % (r, a)))
+    out.append("  // r = a*b + c, small integer b: modmli + modadd fused (rfc7748.c:209,212)\n")
+    out.append(_block_fn(plan, "mla", blocks["mla"], "%s, %s, uint32_t b, %s" % (r, a, _arr("c", L, True))))
     out.append("  // n = a+b (pseudo.py:286-304)\n")
     out.append(_block_fn(plan, "add", blocks["add"], "%s, %s, %s" % (r, a, b)))
     out.append("  // n = a-b (pseudo.py:307-326)\n")

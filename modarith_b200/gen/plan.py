@@ -25,6 +25,7 @@ against Python bignum arithmetic at generation time (`self_check`).
 """
 from __future__ import annotations
 
+import os
 import random
 
 from ..primes import Prime
@@ -56,6 +57,8 @@ class Plan:
         self.L = (prime.nbits + 31) // 32
         self.bound = 1 << (32 * self.L)      # exclusive bound on stored values (overridden)
         self.R = 1                           # Montgomery factor (1 = plain residues)
+        # launch bound of the ladder kernel (measured on B200: X25519 4 CTAs/SM = 110 regs, no spill)
+        self.ladder_minblocks = int(os.environ.get("MAB_MINBLOCKS_" + prime.name, 4 if self.L <= 8 else 2))
 
     # -- representation -----------------------------------------------------
     def to_internal(self, v):                # field value -> stored integer
@@ -70,6 +73,7 @@ class Plan:
             "mul": self.build_mul(),
             "sqr": self.build_sqr(),
             "mli": self.build_mli(),
+            "mla": self.build_mla(),
             "add": self.build_add(),
             "sub": self.build_sub(neg=False),
             "neg": self.build_sub(neg=True),
@@ -108,6 +112,16 @@ class Plan:
         (a,) = self._io(asm, ["a"])
         asm.inp("b")
         T = satmul.times_small(asm, a, "b")
+        self._outs(asm, self.reduce_small(asm, T))
+        return asm
+
+    def build_mla(self):
+        """r = a*b + c for a small integer b: modmli fused with the modadd that follows it in the
+        ladder step (rfc7748.c:209,212: z2 = a24*E + AA)."""
+        asm = Asm(self.name + ".mla")
+        a, c = self._io(asm, ["a", "c"])
+        asm.inp("b")
+        T = satmul.times_small_add(asm, a, "b", c)
         self._outs(asm, self.reduce_small(asm, T))
         return asm
 
@@ -161,6 +175,9 @@ class Plan:
             for bb in (0, 1, 2, 121665, 39081, M32, y & M32):
                 r, _ = self.run("mli", a=ax, b=bb)
                 assert r < B and r % p == x * bb % p, ("mli", hex(x), bb)
+            for bb in (0, 1, 121665, 39081, (1 << 31) - 1):
+                r, _ = self.run("mla", a=ax, c=ay, b=bb)
+                assert r < B and r % p == (x * bb + y) % p, ("mla", hex(x), hex(y), bb)
             r, _ = self.run("add", a=ax, b=ay)
             assert r < B and r % p == (x + y) % p, ("add", hex(x), hex(y))
             r, _ = self.run("sub", a=ax, b=ay)
@@ -220,16 +237,41 @@ class PseudoMersenne(Plan):
         for k in range(start, L):
             asm.add(o[k], r[k], 0, cin=True, cout=True)
         asm.add(c2, 0, 0, cin=True)
-        # a second wrap leaves a tiny value, so this cannot carry (interpreter checks)
+        # a second wrap leaves a tiny value (< c*fold), so this cannot carry past word 0
+        # (word 1 when c is a full word); the interpreter checks
         f = asm.tmp()
+        if wide:
+            g = asm.tmp()
+            asm.madlo(f, c2, self.fold, o[0], cout=True)
+            asm.add(g, o[1], 0, cin=True)
+            return [f, g] + o[2:]
         asm.madlo(f, c2, self.fold, o[0])
         return [f] + o[1:]
 
     def reduce_wide(self, asm, T):
-        """2L words -> L words: lo + fold*hi with two even/odd wide chains
-        (second_pass of pseudo.py:557-611 restated for a saturated radix)."""
+        """2L words -> L words: lo + fold*hi (second_pass of pseudo.py:557-611 restated for a
+        saturated radix).  MAB_FOLD=imad: two even/odd wide multiply chains on the multiplier
+        pipe; MAB_FOLD=alu: shift-and-add on the ALU pipe (fold = 38 = 2^5+2^2+2^1), which
+        frees 8 IMAD.WIDE slots per reduction at the price of ~54 ALU instructions."""
         L = self.L
         lo, hi = T[:L], T[L:]
+        if os.environ.get("MAB_FOLD", "imad") == "alu":
+            acc = list(lo) + [0]
+            for sh in [k for k in range(31, -1, -1) if (self.fold >> k) & 1]:
+                S = []
+                for k in range(L + 1):
+                    d = asm.tmp()
+                    if k == 0:
+                        asm.shl(d, hi[0], sh) if sh else asm.mov(d, hi[0])
+                    elif k == L:
+                        asm.shr(d, hi[L - 1], 32 - sh) if sh else asm.mov(d, 0)
+                    else:
+                        asm.shfl(d, hi[k - 1], hi[k], sh) if sh else asm.mov(d, hi[k])
+                    S.append(d)
+                new = asm.tmp(L + 1)
+                asm.add_chain(new, acc, S)
+                acc = new
+            return self._fold_carry(asm, acc[:L], acc[L])
         r = asm.tmp(L + 1)
         cur = list(lo) + [0]
         # even windows (0,1),(2,3).. take hi[0],hi[2]..; odd windows (1,2).. take hi[1],hi[3]..
@@ -246,6 +288,62 @@ class PseudoMersenne(Plan):
     def reduce_small(self, asm, T):
         """L+1 words (top word < 2^32) -> L words."""
         return self._fold_carry(asm, T[:self.L], T[self.L], wide=True)
+
+    # -- split fold: keeps every 64-bit window on the register pair it was accumulated in --------
+    def _fold_split(self, asm, lo_even, hi, lo_odd=None):
+        """lo_even[0..L-1] + 2^32*lo_odd + fold * hi[0..L-1]  ->  L words.
+
+        Even words of `hi` fold onto the even-aligned windows (0,1),(2,3).. of lo_even with one
+        wide carry chain; odd words fold onto the odd-aligned windows (1,2),(3,4).. of lo_odd
+        (the product's ODD accumulator array, or fresh registers), so no window changes its
+        register pairing (ptxas otherwise re-pairs with ~8 MOVs per reduction); the two results
+        are merged by one add-with-carry chain."""
+        L, f = self.L, self.fold
+        assert L % 2 == 0
+        r = asm.tmp(L)
+        ce = asm.tmp()
+        ev = [(r[k], r[k + 1], hi[k], f, lo_even[k], lo_even[k + 1]) for k in range(0, L, 2)]
+        asm.wide_chain(ev, last_carry_to=(ce, 0))
+        o = {k: asm.tmp() for k in range(1, L + 1)}
+        if lo_odd is None:
+            for k in range(1, L, 2):
+                asm.mullo(o[k], hi[k], f)
+                asm.mulhi(o[k + 1], hi[k], f)
+        else:
+            od = [(o[k], o[k + 1], hi[k], f, lo_odd[k], lo_odd[k + 1] if k + 1 < L else 0) for k in range(1, L, 2)]
+            asm.wide_chain(od, last_carry_to=None)
+        res = [r[0]] + asm.tmp(L - 1)
+        top = asm.tmp()
+        for k in range(1, L):
+            asm.add(res[k], r[k], o[k], cin=(k > 1), cout=True)
+        asm.add(top, ce, o[L], cin=True, cout=False)
+        return self._fold_carry(asm, res, top)
+
+    def build_mul(self):
+        if os.environ.get("MAB_FOLD", "split") != "split":
+            return super().build_mul()
+        asm = Asm(self.name + ".mul")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        E, O = satmul.product_eo(asm, a, b)
+        # U = high halves merged (the low halves stay apart until after the fold)
+        U = asm.tmp(L)
+        for k in range(L):
+            asm.add(U[k], E.src(L + k), O.src(L + k), cin=(k > 0), cout=(k < L - 1))
+        lo_even = [E.src(k) for k in range(L)]
+        lo_odd = {k: O.src(k) for k in range(1, L)}
+        self._outs(asm, self._fold_split(asm, lo_even, U, lo_odd))
+        return asm
+
+    def build_sqr(self):
+        if os.environ.get("MAB_FOLD", "split") != "split":
+            return super().build_sqr()
+        asm = Asm(self.name + ".sqr")
+        (a,) = self._io(asm, ["a"])
+        L = self.L
+        T = satmul.square(asm, a)
+        self._outs(asm, self._fold_split(asm, T[:L], T[L:], None))
+        return asm
 
     def build_add(self):
         asm = Asm(self.name + ".add")

@@ -21,19 +21,37 @@ lost carry) to hold only a few carry bits when they are written.
 """
 from __future__ import annotations
 
+import os
+
 from .ptx import Asm
+
+M32 = 0xFFFFFFFF
+# generator tuning knobs (kernel experiments; defaults are what measured best on B200)
+SMART_CAPTURE = os.environ.get("MAB_CAPTURE", "smart") == "smart"
+ZERO_REG = os.environ.get("MAB_ZERO", "lit") == "reg"
 
 
 class _Acc:
-    """Accumulator words that start as the literal 0 until first written."""
+    """Accumulator words that start as the literal 0 until first written.  `ub` tracks an
+    upper bound of every word so that carry captures which are provably zero are not emitted
+    (the interpreter in ptx.py re-checks every such claim on concrete values)."""
 
     def __init__(self, asm: Asm, n: int):
         self.asm = asm
         self.reg = [asm.tmp() for _ in range(n)]
         self.live = [False] * n
+        self.ub = [0] * n
+        self._zero = None
 
     def src(self, k):
-        return self.reg[k] if self.live[k] else 0
+        if self.live[k]:
+            return self.reg[k]
+        if ZERO_REG:
+            if self._zero is None:
+                self._zero = self.asm.tmp()
+                self.asm.mov(self._zero, 0)
+            return self._zero
+        return 0
 
     def dst(self, k):
         self.live[k] = True
@@ -50,15 +68,23 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
         for s, a, b in prods:
             asm.mullo(acc.dst(s), a, b)
             asm.mulhi(acc.dst(s + 1), a, b)
+            acc.ub[s] = M32
+            acc.ub[s + 1] = M32 - 1
         return
     slots = []
+    cin = 0
     for s, a, b in prods:
         clo, chi = acc.src(s), acc.src(s + 1)
         slots.append((acc.dst(s), acc.dst(s + 1), a, b, clo, chi))
+        vmax = ((acc.ub[s + 1] << 32) | acc.ub[s]) + M32 * M32 + cin      # window after this product
+        cin = 1 if vmax >> 64 else 0
+        acc.ub[s] = M32
+        acc.ub[s + 1] = M32 if cin else (vmax >> 32)
     top = prods[-1][0] + 2
-    if top < nwords:
+    if top < nwords and (cin or not SMART_CAPTURE):
         c = acc.src(top)
         asm.wide_chain(slots, last_carry_to=(acc.dst(top), c))
+        acc.ub[top] = min(M32, acc.ub[top] + 1)
     else:
         asm.wide_chain(slots, last_carry_to=None)
 
@@ -80,8 +106,9 @@ def _merge(asm: Asm, E: _Acc, O: _Acc, nwords):
     return T
 
 
-def product(asm: Asm, a, b):
-    """Return the 2L words (registers) of a*b; a, b are lists of L register names."""
+def product_eo(asm: Asm, a, b):
+    """a*b as the two unmerged accumulator arrays: value = E + O (2L words each; word k of
+    either array is `X.src(k)`, the literal 0 where never written)."""
     L = len(a)
     assert len(b) == L
     n = 2 * L
@@ -91,7 +118,13 @@ def product(asm: Asm, a, b):
         od = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 1]
         _row_chain(asm, E, ev, n)
         _row_chain(asm, O, od, n)
-    return _merge(asm, E, O, n)
+    return E, O
+
+
+def product(asm: Asm, a, b):
+    """Return the 2L words (registers) of a*b; a, b are lists of L register names."""
+    E, O = product_eo(asm, a, b)
+    return _merge(asm, E, O, 2 * len(a))
 
 
 def square(asm: Asm, a):
@@ -150,3 +183,24 @@ def times_small(asm: Asm, a, b):
     asm.add(d, hi[L - 1], 0, cin=True, cout=False)
     T.append(d)
     return T
+
+
+def times_small_add(asm: Asm, a, b, c):
+    """Return L+1 words of a*b + c for one 32-bit multiplier b: even limbs accumulate onto the
+    even-aligned windows of c with one wide carry chain, odd limbs are independent wide multiplies,
+    and one add-with-carry chain merges the two (L even)."""
+    L = len(a)
+    assert L % 2 == 0 and len(c) == L
+    t = [asm.tmp() for _ in range(L)]
+    ce = asm.tmp()
+    asm.wide_chain([(t[k], t[k + 1], a[k], b, c[k], c[k + 1]) for k in range(0, L, 2)], last_carry_to=(ce, 0))
+    o = {k: asm.tmp() for k in range(1, L + 1)}
+    for k in range(1, L, 2):
+        asm.mullo(o[k], a[k], b)
+        asm.mulhi(o[k + 1], a[k], b)
+    res = [t[0]] + [asm.tmp() for _ in range(L - 1)]
+    top = asm.tmp()
+    for k in range(1, L):
+        asm.add(res[k], t[k], o[k], cin=(k > 1), cout=True)
+    asm.add(top, ce, o[L], cin=True, cout=False)
+    return res + [top]

@@ -11,7 +11,9 @@ import os
 from ctypes import c_char_p, c_int, c_size_t, c_uint, c_void_p, POINTER, c_float, c_double, c_longlong
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(PKG, "libmodarith_b200.so")
+# MODARITH_B200_LIB selects an alternative build of the SAME library (kernel-tuning experiments,
+# tools/variants.py); it is never a different backend.
+LIBPATH = os.environ.get("MODARITH_B200_LIB") or os.path.join(PKG, "libmodarith_b200.so")
 
 PRIMES = ("X25519", "X448", "NIST256")
 CURVES = ("X25519", "X448")
@@ -27,6 +29,7 @@ FIELD_SIGNATURES = {
     "modneg": [_P, _P],
     "modmul": [_P, _P, _P],
     "modsqr": [_P, _P],
+    "bench_modmul": [_P, _P, _P, c_uint],
     "modmli": [_P, c_int, _P],
     "modcpy": [_P, _P],
     "modnsqr": [_P, c_int],
@@ -77,6 +80,8 @@ def load() -> ctypes.CDLL:
     lib.mab_products.argtypes = [c_char_p, c_char_p]
     lib.mab_products.restype = c_longlong
     lib.mab_imad_peak.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_double), c_void_p]
+    lib.mab_pipe_probe.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int),
+                                   POINTER(c_int), c_void_p]
     for P in PRIMES:
         for name, lead in FIELD_SIGNATURES.items():
             fn = getattr(lib, "mab_%s_%s" % (P, name))
@@ -95,7 +100,8 @@ def load() -> ctypes.CDLL:
 
 def exported_symbols():
     """Every symbol include/modarith_b200.h declares (used by the CPU-side ABI test)."""
-    syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak"]
+    syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak",
+            "mab_pipe_probe", "mab_release_workspaces"]
     for P in PRIMES:
         syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
     for P in CURVES:
