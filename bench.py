@@ -96,7 +96,7 @@ def cpu_baseline(sample_keys):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -109,12 +109,14 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples whose timestamp falls inside [t_begin, t_end] (time.time() values
+        bracketing the timed region; the sampler itself is started before the warm-up)."""
         if self.proc is None:
             return None
         try:
@@ -128,10 +130,18 @@ class ClockSampler:
         self.f.close()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
+            if t_begin is not None:
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                    continue
             try:
                 sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
             except ValueError:
@@ -326,20 +336,22 @@ def main():
         parity = bool(np.array_equal(out0[:m].cpu().numpy(), want))
 
     # ---- device-resident throughput --------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # running before the warm-up so it is sampling by the timed region
     for w in range(args.warmup):
         rfc7748(CURVE, dk[w % NSETS], du[w % NSETS], dv[w % NSETS])
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for s in range(args.steps):
         rfc7748(CURVE, dk[s % NSETS], du[s % NSETS], dv[s % NSETS])
     e1.record()
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = args.steps
 
     # ---- end to end: host buffers through the C ABI (H2D + ladder + D2H inside the timed region) --

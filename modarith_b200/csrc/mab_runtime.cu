@@ -32,14 +32,15 @@ template <int VARIANT> __global__ void __launch_bounds__(256) k_imad_peak(const 
       } else if (VARIANT == 1) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(x), "r"(y));
-          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi[c]) : "r"(y), "r"(x));
+          // the accumulator is also a multiplicand so that nothing is loop-invariant
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[c]) : "r"(x), "r"(y));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(hi[c]) : "r"(y), "r"(x));
         }
       } else if (VARIANT == 2) {
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
-          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(x), "r"(y));
-          asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[c]) : "r"(y), "r"(x));
+          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(lo[c]) : "r"(x), "r"(y));
+          asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(hi[c]) : "r"(y), "r"(x));
         }
       } else if (VARIANT == 3) {
         // two carry chains of NCH/2 wide multiply-accumulates each, as in the field multiplier
