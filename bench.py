@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="keys in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the X448 / P-256 side measurements")
+    ap.add_argument("--parity-keys", type=int, default=2048,
+                    help="keys of rank 0's first step checked against the reference build before timing")
     return ap.parse_args()
 
 
@@ -331,8 +333,8 @@ def main():
     out0 = rfc7748(CURVE, dk[0], du[0], dv[0])
     torch.cuda.synchronize()
     if ref is not None:
-        m = 2048
-        _, want = time_reference(ref, hk[0][:m].numpy(), hu[0][:m].numpy(), 0)
+        m = min(args.parity_keys, n_local)
+        _, want = time_reference(ref, hk[0][:m].numpy(), hu[0][:m].numpy(), os.cpu_count() or 1)
         parity = bool(np.array_equal(out0[:m].cpu().numpy(), want))
 
     # ---- device-resident throughput --------------------------------------------------------------
@@ -442,6 +444,7 @@ def main():
                     "api": "mab_X25519_rfc7748_host (pinned host buffers, 3-stream chunked pipeline)"},
             "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
             "roofline": roof, "cpu_baseline": base, "clocks": clocks, "parity_spot_check": parity,
+            "parity_keys": min(args.parity_keys, n_local),
             "gather_ms": gather_ms_max if world > 1 else None, "gpu": props.name, "sms": props.multi_processor_count,
             "extra": extra,
         }

@@ -21,6 +21,7 @@ struct F_X448 {
   static constexpr bool MONTGOMERY = false;
   static constexpr int PRO_SQR = 445, PRO_MUL = 14;
   static constexpr int LADDER_MINBLOCKS = 2;   // resident 128-thread CTAs per SM for k_rfc7748
+  static constexpr bool LADDER_STASH = true;   // scalar and x1 in shared memory (see rfc7748_sm100.cuh)
   static constexpr bool HAS_CURVE = true;
   static constexpr uint32_t A24 = 39081;
   static constexpr int COF = 2;

@@ -191,6 +191,12 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748(const uint8_t*
   uint32_t k[L], u[L], out[L];
   aos_ld<L>(k, bk, i, align);
   aos_ld<L>(u, bu, i, align);
-  Rfc7748<F>::scalarmult(out, k, u);
+  if constexpr (F::LADDER_STASH) {
+    // word j of this thread's column at stash[j][threadIdx.x]: consecutive threads, consecutive banks
+    __shared__ uint32_t stash[2 * L][MAB_LADDER_THREADS];
+    Rfc7748<F>::scalarmult(out, k, u, &stash[0][threadIdx.x], MAB_LADDER_THREADS);
+  } else {
+    Rfc7748<F>::scalarmult(out, k, u);
+  }
   aos_st<L>(bv, i, align, out);
 }

@@ -23,7 +23,12 @@ template <class F> struct Rfc7748 {
   }
 
   // One scalar multiplication.  k, u: little-endian byte strings as words; out likewise.
-  static MAB_DEV void scalarmult(uint32_t (&out)[L], uint32_t (&k)[L], uint32_t (&u)[L]) {
+  // `stash`: optional per-thread column of 2*L words (element j at stash[j*pitch]) in shared memory.
+  // When given (F::LADDER_STASH), the scalar and x1 -- read once per 32 steps / once per step -- live
+  // there instead of in 2*L registers, which buys the 14-limb X448 ladder a third warp per
+  // sub-partition; nullptr keeps everything in registers.
+  static MAB_DEV void scalarmult(uint32_t (&out)[L], uint32_t (&k)[L], uint32_t (&u)[L],
+                                 uint32_t* stash = nullptr, int pitch = 0) {
     // mask() (rfc7748.c:148-152,172): drop the bits above Nbits in the top byte of u
     constexpr int rbits = (F::NBITS % 8) ? (F::NBITS % 8) : 8;
     u[L - 1] &= ((((1u << rbits) - 1u) << 24) | 0x00ffffffu);
@@ -41,11 +46,15 @@ template <class F> struct Rfc7748 {
     // no dynamically indexed register (bit(), rfc7748.c:144-146, indexes a byte array instead).
     constexpr int topbits = F::NBITS - 32 * (L - 1);        // bits of the scalar held by the top word
     if (topbits < 32) k[L - 1] <<= (32 - topbits);
+    if (stash) {
+#pragma unroll
+      for (int j = 0; j < L; j++) { stash[j * pitch] = k[j]; stash[(L + j) * pitch] = x1[j]; }
+    }
 
     uint32_t swap = 0;
     MAB_NOUNROLL
     for (int w = L - 1; w >= 0; w--) {           // rfc7748.c:186-221, bits Nbits-1 .. 0
-      uint32_t kw = k[L - 1];
+      uint32_t kw = stash ? stash[w * pitch] : k[L - 1];
       const int nb = (w == L - 1) ? topbits : 32;
       MAB_NOUNROLL
       for (int bi = 0; bi < nb; bi++) {
@@ -69,14 +78,23 @@ template <class F> struct Rfc7748 {
       F::sub(z3, D, C);
       F::sqr(x3, x3);                            // x3 = (DA+CB)^2
       F::sqr(z3, z3);
-      F::mul(z3, z3, x1);                        // z3 = x1*(DA-CB)^2
+      if (stash) {
+        uint32_t t1[L];
+#pragma unroll
+        for (int j = 0; j < L; j++) t1[j] = stash[(L + j) * pitch];
+        F::mul(z3, z3, t1);                      // z3 = x1*(DA-CB)^2
+      } else {
+        F::mul(z3, z3, x1);
+      }
       F::mul(x2, A, B);                          // x2 = AA*BB
       F::sub(B, A, B);                           // E = AA-BB
       F::mla(z2, B, F::A24, A);                  // a24*E + AA  (modmli + modadd fused)
       F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
       }
+      if (!stash) {
 #pragma unroll
-      for (int j = L - 1; j > 0; j--) k[j] = k[j - 1];
+        for (int j = L - 1; j > 0; j--) k[j] = k[j - 1];
+      }
     }
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);

@@ -70,6 +70,8 @@ def emit_field_header(plan: Plan) -> str:
     out.append("  static constexpr int PRO_SQR = %d, PRO_MUL = %d;\n" % (nsq, nmu))
     out.append("  static constexpr int LADDER_MINBLOCKS = %d;   // resident 128-thread CTAs per SM for k_rfc7748\n"
                % plan.ladder_minblocks)
+    out.append("  static constexpr bool LADDER_STASH = %s;   // scalar and x1 in shared memory (see rfc7748_sm100.cuh)\n"
+               % ("true" if plan.ladder_stash else "false"))
     if P.a24 is not None:
         out.append("  static constexpr bool HAS_CURVE = true;\n")
         out.append("  static constexpr uint32_t A24 = %d;\n" % P.a24)
