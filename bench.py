@@ -77,10 +77,25 @@ def time_reference(lib, k, u, threads):
     return time.perf_counter() - t0, out
 
 
+def cpu_baseline_port(sample_keys):
+    """Fallback when oracle/_ref has not been built: the plain-C restatement oracle/oracle.c."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    n = sample_keys if sample_keys > 0 else 2048
+    k, u = make_inputs(n, 7748)
+    c_oracle.rfc7748_batch(CURVE, k[:64], u[:64])
+    t0 = time.perf_counter()
+    c_oracle.rfc7748_batch(CURVE, k, u)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "scalar-mults/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "first %d of the 2^20 PCG64(7748) raw key/point pairs; oracle/oracle.c (generic schoolbook "
+                      "restatement, OpenMP over all cores) -- oracle/_ref was not available" % n}
+
+
 def cpu_baseline(sample_keys):
     lib = load_reference()
     if lib is None:
-        return None
+        return cpu_baseline_port(sample_keys)
     cores = os.cpu_count() or 1
     k, u = make_inputs(min(4096, sample_keys), 1)
     dt, _ = time_reference(lib, k, u, cores)              # warm-up + rate estimate

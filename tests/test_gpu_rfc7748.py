@@ -68,6 +68,15 @@ def test_random_vs_oracle(curve):
         assert out[i].tobytes() == oracle_rfc7748(curve, k[i].tobytes(), u[i].tobytes()), (curve, i)
 
 
+@pytest.mark.parametrize("curve,n", [("X25519", 2048), ("X448", 512)])
+def test_random_vs_c_oracle(curve, n):
+    """A mid-size batch against the plain-C restatement (oracle/oracle.c), every element."""
+    import c_oracle
+    nb = PRIMES[curve].nbytes
+    k, u = util.random_bytes(81, n, nb), util.random_bytes(82, n, nb)
+    assert np.array_equal(_gpu(curve, k, u), c_oracle.rfc7748_batch(curve, k, u))
+
+
 @pytest.mark.parametrize("curve,n", [("X25519", 1 << 16), ("X448", 1 << 14)])
 def test_random_vs_reference_build(ref_libs, curve, n):
     """Every element of a large batch against the reference's own generated C (oracle/_ref)."""

@@ -197,3 +197,54 @@ def test_addchain():
         assert addchain.evaluate(addchain.find_chain(e), 5, 2**127 - 1) == pow(5, e, 2**127 - 1)
     txt = addchain.to_reference_text(addchain.find_chain(PRIMES["X25519"].pe))
     assert txt.startswith("tmp t0") and "shift" in txt and "add z z x" in txt
+
+
+# ---- the plain-C restatement (oracle/oracle.c) -----------------------------------------------------
+def test_c_oracle_golden_and_python_oracle(golden_rfc, golden_field):
+    """oracle.c against every golden vector and against the Python restatement on random inputs."""
+    import c_oracle
+    for c in CURVES:
+        g = golden_rfc[c]
+        nb = g["nbytes"]
+        v = g["rfc"]
+        gen = PRIMES[c].generator.to_bytes(nb, "little").hex()
+        rows = g["edge"] + g["random"] + [{"k": v["sk1"], "u": gen, "out": v["pk1"]}, {"k": v["sk2"], "u": gen, "out": v["pk2"]},
+                                          {"k": v["sk1"], "u": v["pk2"], "out": v["shared"]},
+                                          {"k": g["demo"]["alice"], "u": gen, "out": None}]
+        k = np.frombuffer(b"".join(bytes.fromhex(r["k"]) for r in rows), dtype=np.uint8).reshape(-1, nb)
+        u = np.frombuffer(b"".join(bytes.fromhex(r["u"]) for r in rows), dtype=np.uint8).reshape(-1, nb)
+        out = c_oracle.rfc7748_batch(c, k, u)
+        for i, r in enumerate(rows):
+            if r["out"] is not None:
+                assert out[i].tobytes().hex() == r["out"], (c, i)
+        k, u = util.random_bytes(51, 12, nb), util.random_bytes(52, 12, nb)
+        out = c_oracle.rfc7748_batch(c, k, u)
+        for i in range(12):
+            assert out[i].tobytes() == rfc7748(c, k[i].tobytes(), u[i].tobytes())
+    for name, g in golden_field.items():
+        nb = g["nbytes"]
+        a = np.frombuffer(bytes.fromhex("".join(g["a"])), dtype=np.uint8).reshape(-1, nb)
+        b = np.frombuffer(bytes.fromhex("".join(g["b"])), dtype=np.uint8).reshape(-1, nb)
+        for op, res in g["ops"].items():
+            out, st = c_oracle.field_batch(name, op, a, b if op in ("mul", "add", "sub") else None, g["mli_int"])
+            assert [out[i].tobytes().hex() for i in range(a.shape[0])] == res["out"], (name, op)
+            assert list(st) == res["status"], (name, op)
+        F = FieldOracle(name)
+        a, b = util.random_bytes(61, 40, nb), util.random_bytes(62, 40, nb)
+        for op in ("mul", "inv", "sqrt", "sub", "haf", "qr", "pro"):
+            out, st = c_oracle.field_batch(name, op, a, b if op in ("mul", "sub") else None, 0)
+            for i in range(40):
+                av, bv = int.from_bytes(a[i].tobytes(), "big"), int.from_bytes(b[i].tobytes(), "big")
+                v, s = util.oracle_field_op(F, op, av, bv, 0)
+                assert v.to_bytes(nb, "big") == out[i].tobytes() and s == st[i], (name, op, i)
+
+
+def test_c_oracle_against_reference_build(ref_libs):
+    if "X25519" not in ref_libs:
+        pytest.skip("oracle/_ref not built")
+    import c_oracle
+    for c in CURVES:
+        nb = PRIMES[c].nbytes
+        n = 512 if c == "X25519" else 128
+        k, u = util.random_bytes(71, n, nb), util.random_bytes(72, n, nb)
+        assert np.array_equal(c_oracle.rfc7748_batch(c, k, u), util.ref_rfc7748_batch(ref_libs[c], k, u))
