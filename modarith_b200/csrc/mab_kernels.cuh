@@ -183,7 +183,7 @@ template <class F> __global__ void __launch_bounds__(128) k_exp(const uint32_t* 
 #else
 #define MAB_LADDER_BOUNDS(F) __launch_bounds__(MAB_LADDER_THREADS, F::LADDER_MINBLOCKS)
 #endif
-template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
+template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
   constexpr int L = F::L;
   static_assert(F::NBYTES == 4 * L, "byte strings are whole words for the supported curves");
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,9 +194,9 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748(const uint8_t*
   if constexpr (F::LADDER_STASH) {
     // word j of this thread's column at stash[j][threadIdx.x]: consecutive threads, consecutive banks
     __shared__ uint32_t stash[2 * L][MAB_LADDER_THREADS];
-    Rfc7748<F>::scalarmult(out, k, u, &stash[0][threadIdx.x], MAB_LADDER_THREADS);
+    Rfc7748<F>::template scalarmult<VALIDATE>(out, k, u, &stash[0][threadIdx.x], MAB_LADDER_THREADS);
   } else {
-    Rfc7748<F>::scalarmult(out, k, u);
+    Rfc7748<F>::template scalarmult<VALIDATE>(out, k, u);
   }
   aos_st<L>(bv, i, align, out);
 }

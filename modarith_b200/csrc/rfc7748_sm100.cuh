@@ -27,6 +27,10 @@ template <class F> struct Rfc7748 {
   // When given (F::LADDER_STASH), the scalar and x1 -- read once per 32 steps / once per step -- live
   // there instead of in 2*L registers, which buys the 14-limb X448 ladder a third warp per
   // sub-partition; nullptr keeps everything in registers.
+  // VALIDATE = false: the TWIST_SECURE tail (rfc7748.c:225-227); true: the cheap point validation
+  // of the #else branch (rfc7748.c:228-251, eprint 2020/1497) -- the result is forced to zero
+  // when u is not the x-coordinate of a point on the curve.
+  template <bool VALIDATE = false>
   static MAB_DEV void scalarmult(uint32_t (&out)[L], uint32_t (&k)[L], uint32_t (&u)[L],
                                  uint32_t* stash = nullptr, int pitch = 0) {
     // mask() (rfc7748.c:148-152,172): drop the bits above Nbits in the top byte of u
@@ -99,10 +103,42 @@ template <class F> struct Rfc7748 {
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);
 
-    // TWIST_SECURE branch (rfc7748.c:225-227,252): x2/z2 with 0 -> 0
-    uint32_t h[L];
-    F::pro(h, z2);
-    Fd::template inv<true>(z2, z2, h);
+    if (!VALIDATE) {
+      // TWIST_SECURE branch (rfc7748.c:225-227,252): x2/z2 with 0 -> 0
+      uint32_t h[L];
+      F::pro(h, z2);
+      Fd::template inv<true>(z2, z2, h);
+    } else {
+      // rfc7748.c:228-251: one progenitor gives both 1/z2 and the quadratic character of the
+      // curve equation at u; D ends as 1 (valid point) or 0 and multiplies the result
+      uint32_t A[L], B[L], C[L], D[L], E[L], w[L];
+      if (stash) {
+#pragma unroll
+        for (int j = 0; j < L; j++) w[j] = stash[(L + j) * pitch];
+      } else {
+        Fd::cpy(w, x1);
+      }
+      F::mul(B, w, z2);                          // wZ
+      F::mul(A, B, z2);                          // wZ^2
+      F::pro(E, A);                              // y
+      Fd::cpy(C, A);
+      F::mul(D, E, z2);                          // y.Z2
+      F::sqr(D, D);
+      F::mul(D, D, w);                           // w.(y.z2)^2
+#pragma unroll
+      for (int i = 0; i < F::COF - 2; i++) { F::sqr(C, C); F::mul(C, C, A); }
+#pragma unroll
+      for (int i = 0; i < F::COF; i++) F::sqr(E, E);
+      F::mul(C, C, E);
+      F::mul(z2, C, B);
+#pragma unroll
+      for (int i = 0; i < F::COF - 2; i++) F::sqr(D, D);
+      Fd::one(A);
+      F::add(D, D, A);
+      (void)Fd::fsb(D);
+      (void)Fd::shr(D, 1);                       // 1 for QR, else 0
+      F::mul(x2, x2, D);                         // zero for a bad input point
+    }
     F::mul(x2, x2, z2);
     Fd::to_words(out, x2);                       // modexp (rfc7748.c:254)
   }

@@ -18,7 +18,9 @@ from . import lib as _lib
 _NBYTES = {"X25519": 32, "X448": 56}
 
 
-def rfc7748(curve: str, bk, bu, bv=None, device=None):
+def rfc7748(curve: str, bk, bu, bv=None, device=None, validate=False):
+    """validate=True runs the driver as built without TWIST_SECURE (rfc7748.c:228-251): the result is
+    all zero when bu is not on the curve (device tensors only)."""
     if curve not in _NBYTES:
         raise ValueError("unsupported curve %r" % curve)
     lib = _lib.load()
@@ -33,9 +35,11 @@ def rfc7748(curve: str, bk, bu, bv=None, device=None):
         assert bv.is_cuda and bv.is_contiguous() and bv.shape == bk.shape and bv.dtype == torch.uint8
         stream = torch.cuda.current_stream(bk.device).cuda_stream
         with torch.cuda.device(bk.device):
-            _lib.check(getattr(lib, "mab_%s_rfc7748" % curve)(bk.data_ptr(), bu.data_ptr(), bv.data_ptr(), n, stream),
-                       "mab_%s_rfc7748" % curve)
+            name = "mab_%s_rfc7748%s" % (curve, "_validate" if validate else "")
+            _lib.check(getattr(lib, name)(bk.data_ptr(), bu.data_ptr(), bv.data_ptr(), n, stream), name)
         return bv
+    if validate:
+        raise ValueError("validate=True is available for device tensors only")
     # host path
     if not torch.cuda.is_available():
         raise _lib.MabError("modarith_b200 needs a CUDA device: there is no CPU fallback")

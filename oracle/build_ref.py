@@ -39,6 +39,10 @@ OUT = os.path.join(HERE, "_ref")
 TARGETS = [
     # (name, script, prime argument, generic flag, has rfc7748)
     ("X25519", "pseudo.py", "X25519", False, True),          # ladder build: lazy add/sub
+    # the same driver with `#define TWIST_SECURE` removed: the point-validation tail rfc7748.c:228-251
+    # (generic=True: that tail calls modadd/modfsb/modshr on values the lazy add would leave unreduced)
+    ("X25519_validate", "pseudo.py", "X25519", True, True),
+    ("X448_validate", "monty.py", "X448", True, True),
     ("X448", "monty.py", "X448", False, True),
     # field builds (generic=True, the scripts' default): modadd/modsub reduce to < 2p, so a
     # single modexp after them is canonical -- these back the field-level golden vectors
@@ -86,6 +90,9 @@ def build_one(name, script, prime, generic, ladder, cflags):
             with open(os.path.join(REF, "rfc7748.c")) as f:
                 drv = f.read()
             drv = drv.replace("#define COUNT_CLOCKS", "//#define COUNT_CLOCKS", 1)
+            if name.endswith("_validate"):
+                assert drv.count("#define TWIST_SECURE") == 2
+                drv = drv.replace("#define TWIST_SECURE", "//#define TWIST_SECURE")
             marker = "/*** Insert automatically generated code for modulus field.c here ***/"
             assert marker in drv
             unit = drv.replace(marker, marker + "\n" + field, 1)

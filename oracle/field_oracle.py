@@ -202,9 +202,11 @@ class FieldOracle:
         return int((a - b) % self.p == 0)
 
 
-def rfc7748(prime: Prime | str, bk: bytes, bu: bytes) -> bytes:
+def rfc7748(prime: Prime | str, bk: bytes, bu: bytes, twist_secure: bool = True) -> bytes:
     """rfc7748.c:156-256 restated: bv = clamp(bk) * bu on the Montgomery curve, all
-    little-endian byte strings of Nbytes.  TWIST_SECURE branch (rfc7748.c:225-227)."""
+    little-endian byte strings of Nbytes.  twist_secure=True is the TWIST_SECURE branch
+    (rfc7748.c:225-227); False the cheap point validation of the #else branch (rfc7748.c:228-251),
+    whose result is zero when bu is not on the curve."""
     F = FieldOracle(prime)
     P = F.P
     nb, nbits = P.nbytes, P.nbits
@@ -245,7 +247,30 @@ def rfc7748(prime: Prime | str, bk: bytes, bu: bytes) -> bytes:
         x2 = F.modmul(AA, BB)
     x2, x3 = F.modcsw(swap, x2, x3)
     z2, z3 = F.modcsw(swap, z2, z3)
-    A = F.modpro(z2)                              # rfc7748.c:226-227
-    z2 = F.modinv(z2, A)
+    if twist_secure:
+        A = F.modpro(z2)                          # rfc7748.c:226-227
+        z2 = F.modinv(z2, A)
+    else:                                         # rfc7748.c:228-251
+        B = F.modmul(u, z2)
+        A = F.modmul(B, z2)
+        E = F.modpro(A)
+        C = A
+        D = F.modmul(E, z2)
+        D = F.modsqr(D)
+        D = F.modmul(D, u)
+        for _ in range(P.cof - 2):
+            C = F.modsqr(C)
+            C = F.modmul(C, A)
+        for _ in range(P.cof):
+            E = F.modsqr(E)
+        C = F.modmul(C, E)
+        z2 = F.modmul(C, B)
+        for _ in range(P.cof - 2):
+            D = F.modsqr(D)
+        A = F.modone()
+        D = F.modadd(D, A)
+        D, _ = F.modfsb(D)
+        D, _ = F.modshr(1, D)                     # 1 for QR, else 0
+        x2 = F.modmul(x2, D)
     x2 = F.modmul(x2, z2)                         # rfc7748.c:252
     return F.modexp(x2)[::-1]                     # rfc7748.c:254-255

@@ -51,5 +51,6 @@ def _ref(name):
 @pytest.fixture(scope="session")
 def ref_libs():
     """The reference's own generated C (oracle/_ref), when it has been built."""
-    libs = {n: _ref(n) for n in ("X25519", "X448", "NIST256", "X25519_generic", "X448_generic")}
+    libs = {n: _ref(n) for n in ("X25519", "X448", "NIST256", "X25519_generic", "X448_generic",
+                                  "X25519_validate", "X448_validate")}
     return {k: v for k, v in libs.items() if v is not None}

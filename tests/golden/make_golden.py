@@ -12,6 +12,8 @@ Contents
                   298-305,321-333): value after the 5000x2 loop and the DH secret
                 * fixed edge rows (u in {0,1,p-1,p,p+1,2^n-1,generator}, k in {0,all-ones})
                 * 64 random rows per curve (numpy PCG64 seed 7748, raw unclamped bytes)
+                * "validate": 40 random + the edge rows through the driver compiled without
+                  TWIST_SECURE (point-validation tail, rfc7748.c:228-251)
   field.json    per modulus, per operation: inputs (big-endian hex) -> modexp output of the
                 reference's generated 64-bit C, on the edge.py-style operand set
                 (edge.py:341-360 regenerated, not copied) plus 24 random operands
@@ -90,6 +92,11 @@ def curve_vectors(name, sk1, sk2):
     u = rng.integers(0, 256, (64, nb), dtype=np.uint8)
     out["random"] = [{"k": k[i].tobytes().hex(), "u": u[i].tobytes().hex(),
                       "out": call_rfc(lib, nb, k[i].tobytes(), u[i].tobytes()).hex()} for i in range(64)]
+    # the driver built WITHOUT TWIST_SECURE (rfc7748.c:228-251): same inputs, plus the edge rows
+    vlib = ref(name + "_validate")
+    out["validate"] = [{"k": r["k"], "u": r["u"],
+                        "out": call_rfc(vlib, nb, bytes.fromhex(r["k"]), bytes.fromhex(r["u"])).hex()}
+                       for r in out["random"][:40] + out["edge"]]
     return out
 
 

@@ -62,12 +62,17 @@ template <class F> static int sim_op(int op, const uint32_t* pa, const uint32_t*
   return ret;
 }
 
-template <class F> static void sim_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) {
+template <class F, bool VALIDATE = false> static void sim_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) {
   constexpr int L = F::L;
   uint32_t k[L], u[L], out[L];
   memcpy(k, bk, 4 * L);
   memcpy(u, bu, 4 * L);
-  Rfc7748<F>::scalarmult(out, k, u);
+  if (F::LADDER_STASH) {
+    uint32_t stash[2 * L];                       // stands in for the per-thread shared-memory column
+    Rfc7748<F>::template scalarmult<VALIDATE>(out, k, u, stash, 1);
+  } else {
+    Rfc7748<F>::template scalarmult<VALIDATE>(out, k, u);
+  }
   memcpy(bv, out, 4 * L);
 }
 
@@ -77,6 +82,8 @@ int sim_X448_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32
 int sim_NIST256_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_NIST256>(op, a, b, s, r, r2); }
 void sim_X25519_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X25519>(bk, bu, bv); }
 void sim_X448_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X448>(bk, bu, bv); }
+void sim_X25519_rfc7748_validate(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X25519, true>(bk, bu, bv); }
+void sim_X448_rfc7748_validate(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X448, true>(bk, bu, bv); }
 void sim_X25519_rfc7748_batch(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, size_t n) {
   for (size_t i = 0; i < n; i++) sim_rfc7748<F_X25519>(bk + 32 * i, bu + 32 * i, bv + 32 * i);
 }

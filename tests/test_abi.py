@@ -23,14 +23,14 @@ def header_symbols():
     macro = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", h)
     for P in ("X25519", "X448", "NIST256"):
         syms |= {"mab_%s_%s" % (P, m) for m in macro}
-    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host)?)\s*\(", h))
+    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host|_validate)?)\s*\(", h))
     return syms
 
 
 def test_library_exports_every_declared_symbol(built):
     dll = ctypes.CDLL(built)
     want = header_symbols()
-    assert len(want) == 8 + 3 * 31 + 4
+    assert len(want) == 8 + 3 * 31 + 6
     for s in sorted(want):
         assert hasattr(dll, s), s
     assert want == set(mlib.exported_symbols())

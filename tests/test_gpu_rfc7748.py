@@ -44,6 +44,22 @@ def test_golden_vectors(golden_rfc, curve):
             assert out[i].tobytes().hex() == w, (curve, i, rows[i])
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_validation_tail(golden_rfc, ref_libs, curve):
+    """mab_<curve>_rfc7748_validate: the driver as built without TWIST_SECURE (rfc7748.c:228-251)."""
+    from modarith_b200.rfc7748 import rfc7748
+    nb = PRIMES[curve].nbytes
+    k, u, want = _rows(golden_rfc[curve]["validate"], nb)
+    out = rfc7748(curve, torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda(), validate=True).cpu().numpy()
+    assert [out[i].tobytes().hex() for i in range(len(want))] == want
+    key = curve + "_validate"
+    if key in ref_libs:
+        n = 4096
+        k, u = util.random_bytes(101, n, nb), util.random_bytes(102, n, nb)
+        out = rfc7748(curve, torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda(), validate=True).cpu().numpy()
+        assert np.array_equal(out, util.ref_rfc7748_batch(ref_libs[key], k, u))
+
+
 def test_demo_loop_x25519(golden_rfc):
     """rfc7748.c:main: 5000 x 2 chained calls, each output feeding the next."""
     from modarith_b200.rfc7748 import rfc7748

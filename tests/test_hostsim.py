@@ -29,6 +29,17 @@ def test_ladder_golden(hostsim, golden_rfc, curve):
         assert out.raw[:nb].hex() == r["out"], r
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_ladder_validation_tail(hostsim, golden_rfc, curve):
+    """The ladder variant with the point-validation tail (rfc7748.c:228-251)."""
+    nb = golden_rfc[curve]["nbytes"]
+    fn = getattr(hostsim, "sim_%s_rfc7748_validate" % curve)
+    for r in golden_rfc[curve]["validate"]:
+        out = ctypes.create_string_buffer(nb)
+        fn(bytes.fromhex(r["k"]), bytes.fromhex(r["u"]), out)
+        assert out.raw[:nb].hex() == r["out"], r
+
+
 def test_ladder_demo_loop(hostsim, golden_rfc):
     """rfc7748.c:main's 5000x2 chained loop (X25519): every output feeds the next call."""
     d = golden_rfc["X25519"]["demo"]

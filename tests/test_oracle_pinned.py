@@ -64,6 +64,15 @@ def test_rfc7748_edge_and_random_rows(golden_rfc, curve):
         assert rfc7748(curve, bytes.fromhex(r["k"]), bytes.fromhex(r["u"])).hex() == r["out"], r
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_rfc7748_validation_tail(golden_rfc, curve):
+    """rfc7748.c:228-251 (driver built without TWIST_SECURE): zero for points off the curve."""
+    rows = golden_rfc[curve]["validate"]
+    assert 10 < sum(1 for r in rows if int(r["out"], 16) == 0) < len(rows) - 10
+    for r in rows[:30] + rows[40:60]:
+        assert rfc7748(curve, bytes.fromhex(r["k"]), bytes.fromhex(r["u"]), twist_secure=False).hex() == r["out"], r
+
+
 @pytest.mark.parametrize("name", list(PRIMES))
 def test_field_golden(golden_field, name):
     """Field-level vectors produced by the reference's generated 64-bit C (tests/golden/make_golden.py)."""

@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Small batches through every kernel family, for `compute-sanitizer --tool memcheck|racecheck|initcheck`.
+
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+(The reference has no sanitizer story -- SURVEY.md section 5; its CUDA demo has a cross-thread race
+in modcsw/modcmv's `static spint R`, section 2a.  Ragged sizes are used on purpose.)
+"""
+import os
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from modarith_b200 import Field  # noqa: E402
+from modarith_b200.rfc7748 import rfc7748  # noqa: E402
+
+g = torch.Generator(device="cuda").manual_seed(3)
+for curve, nb in (("X25519", 32), ("X448", 56)):
+    n = 257
+    k = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
+    u = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
+    a = rfc7748(curve, k, u)
+    b = rfc7748(curve, k, u, validate=True)
+    h = rfc7748(curve, k.cpu().numpy(), u.cpu().numpy())
+    assert (a.cpu().numpy() == h).all()
+for name in ("X25519", "X448", "NIST256"):
+    F = Field(name)
+    n = 131
+    x, st = F.modimp(torch.randint(0, 256, (n, F.Nbytes), dtype=torch.uint8, device="cuda", generator=g))
+    y, _ = F.modimp(torch.randint(0, 256, (n, F.Nbytes), dtype=torch.uint8, device="cuda", generator=g))
+    r = F.alloc(n)
+    F.modmul(x, y, r); F.modsqr(x, r); F.modadd(x, y, r); F.modsub(x, y, r); F.modneg(x, r)
+    F.modmli(x, 121665, r); F.modinv(x, None, r); F.modsqrt(x, None, r); F.modpro(x, r)
+    F.modqr(None, x); F.modis0(x); F.modis1(x); F.modsign(x); F.modcmp(x, y); F.modfsb(r)
+    F.modhaf(r); F.modshl(3, r); F.modshr(3, r); F.mod2r(77, r); F.modint(5, r); F.modone(r); F.modzer(r)
+    bits = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda", generator=g)
+    F.modcsw(bits, x, y); F.modcmv(bits, x, y); F.nres(x, r); F.redc(x, r); F.modnsqr(r, 3); F.modcpy(x, r)
+    F.modexp(r)
+torch.cuda.synchronize()
+print("sanitize smoke done")
