@@ -74,6 +74,8 @@ MAB_API int mab_pipe_probe(int variant, int iters, int blocks, int threads, floa
 
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
+  /* macros of the generated header (pseudo.py:1403-1407) plus the modpro chain cost; any pointer may be NULL */ \
+  MAB_API int mab_##P##_info(int *nlimbs, int *nbits, int *nbytes, int *pm1d2, int *pro_sqr, int *pro_mul, int *montgomery, int *has_curve); \
   /* modfsb   pseudo.py:272-283   canonicalise in place; was_lt[i]=1 iff stored value was < p (may be NULL) */ \
   MAB_API int mab_##P##_modfsb(uint32_t *n_, int *was_lt, size_t n, size_t stride, void *stream);                 \
   /* modadd   pseudo.py:286-304 */                                                                        \
@@ -133,6 +135,12 @@ MAB_API int mab_pipe_probe(int variant, int iters, int blocks, int threads, floa
 MAB_DECLARE_FIELD(X25519)
 MAB_DECLARE_FIELD(X448)
 MAB_DECLARE_FIELD(NIST256)
+/* Two moduli outside the three hot-path ones, built with the generator's fall-back plan (full Montgomery,
+ * any odd modulus -- monty.py's unshaped case, monty.py:2237-2244): the secp256k1 field prime
+ * (monty.py:2066-2067) and the order of the P-256 group (the reference's "00<decimal>" mode, monty.py:2110-2127).
+ * Further moduli: python -m modarith_b200.build --prime NAME=<expression>  (INTEGRATION.md). */
+MAB_DECLARE_FIELD(SECP256K1)
+MAB_DECLARE_FIELD(NIST256ORDER)
 
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */

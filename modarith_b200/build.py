@@ -22,7 +22,8 @@ OBJDIR = os.path.join(PKG, "build")
 
 NVCC_FLAGS = ["-I", CSRC, "-I", os.path.join(PKG, "..", "include"), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
-UNITS = ["mab_capi_X25519.cu", "mab_capi_X448.cu", "mab_capi_NIST256.cu", "mab_runtime.cu"]
+UNITS = ["mab_capi_X25519.cu", "mab_capi_X448.cu", "mab_capi_NIST256.cu", "mab_capi_SECP256K1.cu",
+         "mab_capi_NIST256ORDER.cu", "mab_runtime.cu"]
 
 
 def _nvcc():
@@ -67,7 +68,7 @@ def build(force=False, verbose=True):
 
     with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)

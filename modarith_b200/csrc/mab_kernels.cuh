@@ -148,13 +148,25 @@ template <int NW> static __device__ __forceinline__ void aos_st(uint8_t* base, s
 // modimp (pseudo.py:1130-1146): big-endian Nbytes -> planes; status[i] = 1 iff value < p
 template <class F> __global__ void __launch_bounds__(128) k_imp(const uint8_t* bytes, uint32_t* r, int* status, size_t n, size_t stride, unsigned align) {
   constexpr int L = F::L;
-  static_assert(F::NBYTES == 4 * L, "byte strings are whole words for the supported moduli");
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t raw[L], w[L], a[L];
-  aos_ld<L>(raw, bytes, i, align);
+  uint32_t w[L], a[L];
+  if constexpr (F::NBYTES == 4 * L) {
+    uint32_t raw[L];
+    aos_ld<L>(raw, bytes, i, align);
 #pragma unroll
-  for (int j = 0; j < L; j++) w[j] = mab_bswap(raw[L - 1 - j]);
+    for (int j = 0; j < L; j++) w[j] = mab_bswap(raw[L - 1 - j]);
+  } else {
+    // Nbytes is not a whole number of words (e.g. 521-bit moduli): byte-wise, most significant first
+    const uint8_t* e = bytes + i * (size_t)F::NBYTES;
+#pragma unroll
+    for (int j = 0; j < L; j++) w[j] = 0;
+#pragma unroll
+    for (int b = 0; b < F::NBYTES; b++) {
+      const int pos = F::NBYTES - 1 - b;
+      w[pos >> 2] |= (uint32_t)e[b] << (8 * (pos & 3));
+    }
+  }
   uint32_t lt = Field<F>::from_words(a, w);
   plane_st<L>(r, stride, i, a);
   if (status) status[i] = (int)lt;
@@ -164,12 +176,22 @@ template <class F> __global__ void __launch_bounds__(128) k_exp(const uint32_t* 
   constexpr int L = F::L;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t a[L], w[L], raw[L];
+  uint32_t a[L], w[L];
   plane_ld<L>(a, ap, stride, i);
   Field<F>::to_words(w, a);
+  if constexpr (F::NBYTES == 4 * L) {
+    uint32_t raw[L];
 #pragma unroll
-  for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(w[j]);
-  aos_st<L>(bytes, i, align, raw);
+    for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(w[j]);
+    aos_st<L>(bytes, i, align, raw);
+  } else {
+    uint8_t* e = bytes + i * (size_t)F::NBYTES;
+#pragma unroll
+    for (int b = 0; b < F::NBYTES; b++) {
+      const int pos = F::NBYTES - 1 - b;
+      e[b] = (uint8_t)(w[pos >> 2] >> (8 * (pos & 3)));
+    }
+  }
 }
 
 // rfc7748 (rfc7748.c:156): bv[i] = clamp(bk[i]) * bu[i], little-endian Nbytes strings

@@ -4,7 +4,7 @@ from __future__ import annotations
 import argparse
 import os
 
-from ..primes import PRIMES, Prime
+from ..primes import PRIMES, ALL_PRIMES, Prime
 from .plan import make_plan
 from .emit import emit_field_header
 
@@ -12,8 +12,8 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 
 
 def resolve(prime: str, family: str) -> Prime:
-    if prime in PRIMES:
-        return PRIMES[prime]
+    if prime in ALL_PRIMES:
+        return ALL_PRIMES[prime]
     if prime[0].isdigit():                      # expression, as pseudo.py:1553-1556
         p = eval(prime, {"__builtins__": {}})
         return Prime("P%d" % p.bit_length(), p, family)
@@ -54,4 +54,4 @@ def main(family: str, argv) -> int:
 
 
 def generate_all(verbose=False):
-    return [generate(P, verbose=verbose) for P in PRIMES.values()]
+    return [generate(P, verbose=verbose) for P in ALL_PRIMES.values()]

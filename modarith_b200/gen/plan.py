@@ -676,12 +676,93 @@ class Montgomery(Plan):
         return asm
 
 
+class MontgomeryFull(Montgomery):
+    """Montgomery form, R = 2^(32L), for ANY odd modulus below 2^(32L) -- the fallback that makes
+    the generator total, as monty.py is for the reference (full Montgomery, ndash != 1:
+    monty.py:740-751,2237-2244; e.g. group orders, monty.py:2110-2127).  Separated-operand REDC:
+
+        Q = T_lo * (-p^-1 mod R)  mod R      L(L+1)/2 wide multiplies by a constant
+        U = Q * p                            L^2 wide multiplies by a constant
+        a*b*R^-1 = (T + U) / R               one 2L-word add chain, one conditional subtraction
+
+    2.5 L^2 wide multiplies per modmul instead of L^2: correct first; interleaving the reduction
+    rows with the product rows (2 L^2 + L) is the known next step.  Stored values are fully
+    reduced, in [0, p)."""
+
+    def __init__(self, prime):
+        Plan.__init__(self, prime)
+        L = self.L
+        assert prime.p % 2 == 1
+        self.R = 1 << (32 * L)
+        self.bound = prime.p
+        self.nprime = (-pow(prime.p, -1, self.R)) % self.R
+        self.R2 = self.R * self.R % prime.p
+        self.d_terms = self.dinv_terms = None
+
+    def _redc(self, asm, T):
+        L = self.L
+        lo = T[:L]
+        Q = satmul.product_low(asm, lo, words(self.nprime, L))
+        U = satmul.product(asm, Q, words(self.p, L))
+        s = asm.tmp(2 * L)
+        top = asm.tmp()
+        asm.add_chain(s, T, U, carry_to=(top, 0))          # low half becomes zero by construction
+        return self._cond_sub_p9(asm, s[L:] + [top])
+
+    def reduce_small(self, asm, T):
+        raise NotImplementedError
+
+    def _small_times(self, asm, a, bname, c=None):
+        """a*b (+c) for a small plain integer b: b is lifted into Montgomery form with one
+        multiplication by R^2 (b*R), then multiplied in; no R factor remains (monty.py:876-978
+        gets there with a Barrett-Dhem estimate instead)."""
+        L = self.L
+        r2 = words(self.R2, L)
+        t = satmul.times_small(asm, r2, bname)                       # R^2 * b  (L+1 words)
+        # Montgomery-reduce R^2*b (< 2^32 * p): pad to 2L words
+        bm = self._redc(asm, t + [0] * (2 * L - (L + 1)))            # = b*R mod p
+        T = satmul.product(asm, a, bm)
+        r = self._redc(asm, T)
+        if c is None:
+            return r
+        s = asm.tmp(L + 1)
+        asm.add_chain(s[:L], r, c, carry_to=(s[L], 0))
+        return self._cond_sub_p9(asm, s)
+
+    def build_mli(self):
+        asm = Asm(self.name + ".mli")
+        (a,) = self._io(asm, ["a"])
+        asm.inp("b")
+        self._outs(asm, self._small_times(asm, a, "b"))
+        return asm
+
+    def build_mla(self):
+        asm = Asm(self.name + ".mla")
+        a, c = self._io(asm, ["a", "c"])
+        asm.inp("b")
+        self._outs(asm, self._small_times(asm, a, "b", c))
+        return asm
+
+
 def make_plan(prime: Prime) -> Plan:
+    """Choose the cheapest plan whose preconditions hold for this modulus (cf. the radix /
+    strategy decisions of pseudo.py:1569-1678 and monty.py:2140-2248); MontgomeryFull accepts
+    any odd modulus, so every prime the reference generators take is covered."""
     p, n = prime.p, prime.nbits
-    if n % 64 == 0 and p == (1 << n) - (1 << (n // 2)) - 1:
-        return GenMersenne(prime)
-    c = (1 << n) - p
     L = (n + 31) // 32
-    if c < (1 << 12) and (c << (32 * L - n)) < (1 << 15):
-        return PseudoMersenne(prime)
-    return Montgomery(prime)
+    c = (1 << n) - p
+    cands = []
+    if n % 64 == 0 and p == (1 << n) - (1 << (n // 2)) - 1 and (n // 2) % 32 == 0:
+        cands.append(GenMersenne)
+    if L % 2 == 0 and c < (1 << 12) and (c << (32 * L - n)) < (1 << 15):
+        cands.append(PseudoMersenne)
+    cands += [Montgomery, MontgomeryFull]
+    err = None
+    for cls in cands:
+        try:
+            plan = cls(prime)
+            plan.build()
+            return plan
+        except (AssertionError, NotImplementedError) as e:
+            err = e
+    raise ValueError("no limb plan for modulus %s: %r" % (prime.name, err))

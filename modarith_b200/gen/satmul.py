@@ -204,3 +204,48 @@ def times_small_add(asm: Asm, a, b, c):
         asm.add(res[k], t[k], o[k], cin=(k > 1), cout=True)
     asm.add(top, ce, o[L], cin=True, cout=False)
     return res + [top]
+
+
+def product_low(asm: Asm, a, b):
+    """Low L words of a*b (mod 2^(32L)); b may hold integer literals (a constant operand).
+    Only the products that reach below word L are formed: L(L+1)/2 wide multiplies, the ones
+    landing on word L-1 as plain 32-bit multiplies."""
+    L = len(a)
+    lo_only = []                       # (a_j, b_i) whose low word lands on word L-1
+    n = L + 1                          # one scratch word above the result absorbs what is dropped
+    E, O = _Acc(asm, n), _Acc(asm, n)
+    for i in range(L):
+        if isinstance(b[i], int) and b[i] == 0:
+            continue
+        ev = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 0 and i + j <= L - 2]
+        od = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 1 and i + j <= L - 2]
+        for acc, prods in ((E, ev), (O, od)):
+            if not prods:
+                continue
+            start = len(asm.ins)
+            _row_chain(asm, acc, prods, n)
+            # whatever leaves the low L words is dropped on purpose
+            for k in range(start, len(asm.ins)):
+                asm.nocheck.add(k)
+        lo_only.append((a[L - 1 - i], b[i]))
+    T = []
+    started = False
+    for k in range(L):
+        e, o = E.src(k), O.src(k)
+        if not started and (e == 0 or o == 0) and (isinstance(e, int) or isinstance(o, int)):
+            T.append(o if (isinstance(e, int) and e == 0) else e)
+            continue
+        d = asm.tmp()
+        if k == L - 1:
+            asm.nocheck.add(len(asm.ins))
+        asm.add(d, e, o, cin=started, cout=(k < L - 1))
+        started = True
+        T.append(d)
+    top = T[L - 1]
+    for (x, y) in lo_only:
+        d = asm.tmp()
+        asm.nocheck.add(len(asm.ins))
+        asm.madlo(d, x, y, top)
+        top = d
+    T[L - 1] = top
+    return T

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # tools/variants.py); it is never a different backend.
 LIBPATH = os.environ.get("MODARITH_B200_LIB") or os.path.join(PKG, "libmodarith_b200.so")
 
-PRIMES = ("X25519", "X448", "NIST256")
+PRIMES = ("X25519", "X448", "NIST256", "SECP256K1", "NIST256ORDER")
 CURVES = ("X25519", "X448")
 
 _P = c_void_p          # device pointers travel as integers
@@ -23,6 +23,7 @@ _TAIL = [c_size_t, c_size_t, c_void_p]      # n, stride, stream
 
 # name -> leading argument types (the reference's argument order), SURVEY.md 8a
 FIELD_SIGNATURES = {
+    "info": [POINTER(c_int)] * 8,
     "modfsb": [_P, _P],
     "modadd": [_P, _P, _P],
     "modsub": [_P, _P, _P],
@@ -85,7 +86,7 @@ def load() -> ctypes.CDLL:
     for P in PRIMES:
         for name, lead in FIELD_SIGNATURES.items():
             fn = getattr(lib, "mab_%s_%s" % (P, name))
-            fn.argtypes = lead + _TAIL
+            fn.argtypes = lead + ([] if name == "info" else _TAIL)
             fn.restype = c_int
     for P in CURVES:
         fn = getattr(lib, "mab_%s_rfc7748" % P)
@@ -120,10 +121,24 @@ def check(code: int, what: str = ""):
 
 def params(prime: str):
     lib = load()
-    v = [c_int() for _ in range(5)]
-    check(lib.mab_params(prime.encode(), *[ctypes.byref(x) for x in v]), "mab_params")
-    return dict(zip(("wordlength", "nlimbs", "radix", "nbits", "nbytes"), [x.value for x in v]))
+    v = [c_int() for _ in range(8)]
+    check(getattr(lib, "mab_%s_info" % prime)(*[ctypes.byref(x) for x in v]), "mab_%s_info" % prime)
+    d = dict(zip(("nlimbs", "nbits", "nbytes", "pm1d2", "pro_sqr", "pro_mul", "montgomery", "has_curve"),
+                 [x.value for x in v]))
+    d.update(wordlength=32, radix=32)
+    return d
 
 
 def products(prime: str, what: str) -> int:
-    return int(load().mab_products(prime.encode(), what.encode()))
+    """Algorithmic 32x32->64 limb products of one call."""
+    r = int(load().mab_products(prime.encode(), what.encode()))
+    if r != -1 or prime in ("X25519", "X448", "NIST256"):
+        return r
+    q = params(prime)
+    L = q["nlimbs"]
+    M, S = L * L, L * (L + 1) // 2
+    pro = q["pro_sqr"] * S + q["pro_mul"] * M
+    k = q["pm1d2"]
+    table = {"modmul": M, "modsqr": S, "modmli": L, "modpro": pro,
+             "modinv": pro + (k - 1) * (S + M) + (k + 1) * S + M}
+    return table.get(what, -1)

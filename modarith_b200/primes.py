@@ -57,4 +57,13 @@ X25519 = Prime("X25519", 2**255 - 19, "pseudo", a24=121665, cof=3, generator=9)
 X448 = Prime("X448", 2**448 - 2**224 - 1, "monty", a24=39081, cof=2, generator=5)
 NIST256 = Prime("NIST256", 2**256 - 2**224 + 2**192 + 2**96 - 1, "monty")
 
+# the three moduli of the hot path (BASELINE configs)
 PRIMES = {q.name: q for q in (X25519, X448, NIST256)}
+
+# moduli outside the hot path that are built into the library to exercise the generator's fall-back plan
+# (full Montgomery, any odd modulus): a field prime that is NOT exploitable by the cheaper plans
+# (monty.py:2066-2067) and a group order (the reference's "00<decimal>" mode, monty.py:2110-2127)
+SECP256K1 = Prime("SECP256K1", 2**256 - 2**32 - 977, "monty")
+NIST256ORDER = Prime("NIST256ORDER", 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551, "monty")
+EXTRA_PRIMES = {q.name: q for q in (SECP256K1, NIST256ORDER)}
+ALL_PRIMES = dict(PRIMES, **EXTRA_PRIMES)

@@ -49,6 +49,10 @@ TARGETS = [
     ("X25519_generic", "pseudo.py", "X25519", True, False),
     ("X448_generic", "monty.py", "X448", True, False),
     ("NIST256", "monty.py", "NIST256", True, False),
+    # outside the hot path: an unshaped field prime and a group order ("00<decimal>" -> group.c,
+    # monty.py:2110-2127); they back the vectors for the generator's full-Montgomery fall-back plan
+    ("SECP256K1", "monty.py", "SECP256K1", True, False),
+    ("NIST256ORDER", "monty.py", "00115792089210356248762697446949407573529996955224135760342422259061068512044369", True, False),
 ]
 
 
@@ -83,7 +87,8 @@ def build_one(name, script, prime, generic, ladder, cflags):
         log = r.stdout
         if "Passed - OK" not in log:
             raise RuntimeError("reference generator self-test did not pass for %s:\n%s" % (name, log))
-        with open(os.path.join(work, "field.c")) as f:
+        fname = "group.c" if prime.startswith("00") else "field.c"
+        with open(os.path.join(work, fname)) as f:
             field = f.read()
         unit = field
         if ladder:

@@ -7,8 +7,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "liboracle.so")
-PRIME_ID = {"X25519": 0, "X448": 1, "NIST256": 2}
-NBYTES = {"X25519": 32, "X448": 56, "NIST256": 32}
+PRIME_ID = {"X25519": 0, "X448": 1, "NIST256": 2, "SECP256K1": 3, "NIST256ORDER": 4}
+NBYTES = {"X25519": 32, "X448": 56, "NIST256": 32, "SECP256K1": 32, "NIST256ORDER": 32}
 OPS = {"mul": 0, "sqr": 1, "inv": 2, "sqrt": 3, "add": 4, "sub": 5, "neg": 6, "pro": 7, "id": 8, "mli": 9,
        "haf": 10, "qr": 11}
 _lib = None

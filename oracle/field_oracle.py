@@ -24,7 +24,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from modarith_b200.primes import PRIMES, Prime  # noqa: E402  (data tables only)
+from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime  # noqa: E402  (data tables only)
 from modarith_b200 import addchain as _ac  # noqa: E402
 
 

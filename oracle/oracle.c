@@ -33,7 +33,7 @@ typedef struct {
     uint32_t a24; int cof; uint32_t gen;   /* rfc7748.c:120-132 */
 } fld;
 
-static fld F25519, F448, FP256;
+static fld F25519, F448, FP256, FSECP, FORD;
 static int inited = 0;
 
 /* ---- tiny multiword helpers (little-endian 32-bit words) ------------------------------------- */
@@ -182,18 +182,28 @@ static void finish(fld *f) {
     f->k = 0; while (!bitw(pm1, f->k)) f->k++;
     uint32_t e[MAXW]; memset(e, 0, sizeof e); e[0] = 1u << f->k;
     subw(f->pe, pm1, e, MAXW); shr_words(f->pe, MAXW, f->k + 1);
-    /* root of unity: p-1 (k=1), 2^((p-1)/4) (k=2)   [pseudo.py:1619-1622; k>2 not needed here] */
+    /* root of unity (pseudo.py:1616-1627): p-1 (k=1), 2^((p-1)/4) (k=2), qnr^((p-1)/2^k) (k>2) */
     if (f->k == 1) memcpy(f->roi, pm1, 4 * MAXW);
     else {
-        uint32_t ex[MAXW]; memcpy(ex, pm1, 4 * MAXW); shr_words(ex, MAXW, 2);
-        uint32_t acc[MAXW], two[MAXW]; f_set(f, acc, 1); f_set(f, two, 2);
-        for (int i = 32 * f->nw - 1; i >= 0; i--) { f_sqr(f, acc, acc); if (bitw(ex, i)) f_mul(f, acc, acc, two); }
+        uint32_t base = 2;
+        if (f->k > 2) {                       /* smallest quadratic non-residue */
+            uint32_t half[MAXW]; memcpy(half, pm1, 4 * MAXW); shr_words(half, MAXW, 1);
+            for (;; base++) {
+                uint32_t acc[MAXW], b[MAXW]; f_set(f, acc, 1); f_set(f, b, base);
+                for (int i = 32 * f->nw - 1; i >= 0; i--) { f_sqr(f, acc, acc); if (bitw(half, i)) f_mul(f, acc, acc, b); }
+                if (!f_is(f, acc, 1)) break;
+            }
+        }
+        uint32_t ex[MAXW]; memcpy(ex, pm1, 4 * MAXW); shr_words(ex, MAXW, f->k);
+        uint32_t acc[MAXW], b[MAXW]; f_set(f, acc, 1); f_set(f, b, base);
+        for (int i = 32 * f->nw - 1; i >= 0; i--) { f_sqr(f, acc, acc); if (bitw(ex, i)) f_mul(f, acc, acc, b); }
         memcpy(f->roi, acc, 4 * MAXW);
     }
 }
 static void init(void) {
     if (inited) return;
     memset(&F25519, 0, sizeof F25519); memset(&F448, 0, sizeof F448); memset(&FP256, 0, sizeof FP256);
+    memset(&FSECP, 0, sizeof FSECP); memset(&FORD, 0, sizeof FORD);
     /* 2^255-19 (pseudo.py:1523-1524) */
     F25519.nbits = 255; for (int i = 0; i < 8; i++) F25519.p[i] = 0xffffffffu; F25519.p[0] = 0xffffffedu; F25519.p[7] = 0x7fffffffu;
     F25519.a24 = 121665; F25519.cof = 3; F25519.gen = 9;
@@ -203,10 +213,17 @@ static void init(void) {
     /* NIST P-256 (monty.py:1966-1967) */
     FP256.nbits = 256;
     { const uint32_t w[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 1, 0xffffffffu}; memcpy(FP256.p, w, sizeof w); }
-    finish(&F25519); finish(&F448); finish(&FP256);
+    /* secp256k1 field prime 2^256-2^32-977 (monty.py:2066-2067); order of the P-256 group (monty.py:2110-2127) */
+    FSECP.nbits = 256; for (int i = 0; i < 8; i++) FSECP.p[i] = 0xffffffffu; FSECP.p[0] = 0xfffffc2fu; FSECP.p[1] = 0xfffffffeu;
+    FORD.nbits = 256;
+    { const uint32_t w[8] = {0xfc632551u, 0xf3b9cac2u, 0xa7179e84u, 0xbce6faadu, 0xffffffffu, 0xffffffffu, 0, 0xffffffffu}; memcpy(FORD.p, w, sizeof w); }
+    finish(&F25519); finish(&F448); finish(&FP256); finish(&FSECP); finish(&FORD);
     inited = 1;
 }
-static const fld *field(int id) { init(); return id == 0 ? &F25519 : id == 1 ? &F448 : &FP256; }
+static const fld *field(int id) {
+    init();
+    return id == 0 ? &F25519 : id == 1 ? &F448 : id == 2 ? &FP256 : id == 3 ? &FSECP : &FORD;
+}
 
 /* ---- exported: batched byte-level drivers (same shape as oracle/ref_shim.c) ------------------------- */
 #define EXPORT __attribute__((visibility("default")))

@@ -30,7 +30,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.join(HERE, "..", "..")
 sys.path.insert(0, ROOT)
-from modarith_b200.primes import PRIMES  # noqa: E402
+from modarith_b200.primes import PRIMES, ALL_PRIMES  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref")
 OPS = {"mul": 0, "sqr": 1, "inv": 2, "sqrt": 3, "add": 4, "sub": 5, "neg": 6, "pro": 7, "id": 8, "mli": 9,
@@ -112,9 +112,9 @@ def edge_operands(P):
 
 
 def field_vectors(name):
-    P = PRIMES[name]
+    P = ALL_PRIMES[name]
     nb = P.nbytes
-    lib = ref(name if name == "NIST256" else name + "_generic")
+    lib = ref(name + "_generic" if name in ("X25519", "X448") else name)
     rng = np.random.Generator(np.random.PCG64(256 + nb))
     edge = edge_operands(P)
     a_vals = list(edge)
@@ -146,7 +146,7 @@ def main():
     }
     with open(os.path.join(HERE, "rfc7748.json"), "w") as f:
         json.dump(rfc, f, indent=1)
-    fld = {name: field_vectors(name) for name in PRIMES}
+    fld = {name: field_vectors(name) for name in ALL_PRIMES}
     with open(os.path.join(HERE, "field.json"), "w") as f:
         json.dump(fld, f, indent=1)
     print("wrote rfc7748.json, field.json")

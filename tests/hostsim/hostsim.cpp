@@ -10,6 +10,8 @@
 #include "gen/field_X25519.cuh"
 #include "gen/field_X448.cuh"
 #include "gen/field_NIST256.cuh"
+#include "gen/field_SECP256K1.cuh"
+#include "gen/field_NIST256ORDER.cuh"
 #include "rfc7748_sm100.cuh"
 
 enum SimOp {
@@ -80,6 +82,8 @@ extern "C" {
 int sim_X25519_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X25519>(op, a, b, s, r, r2); }
 int sim_X448_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X448>(op, a, b, s, r, r2); }
 int sim_NIST256_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_NIST256>(op, a, b, s, r, r2); }
+int sim_SECP256K1_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_SECP256K1>(op, a, b, s, r, r2); }
+int sim_NIST256ORDER_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_NIST256ORDER>(op, a, b, s, r, r2); }
 void sim_X25519_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X25519>(bk, bu, bv); }
 void sim_X448_rfc7748(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X448>(bk, bu, bv); }
 void sim_X25519_rfc7748_validate(const unsigned char* bk, const unsigned char* bu, unsigned char* bv) { sim_rfc7748<F_X25519, true>(bk, bu, bv); }

@@ -21,8 +21,9 @@ def header_symbols():
     h = open(os.path.join(ROOT, "include", "modarith_b200.h")).read()
     syms = set(re.findall(r"\b(mab_[a-z0-9_]+)\s*\(", h))
     macro = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", h)
-    for P in ("X25519", "X448", "NIST256"):
-        syms |= {"mab_%s_%s" % (P, m) for m in macro}
+    for P in re.findall(r"MAB_DECLARE_FIELD\((\w+)\)\n", h):
+        if P != "P":
+            syms |= {"mab_%s_%s" % (P, m) for m in macro}
     syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host|_validate)?)\s*\(", h))
     return syms
 
@@ -30,7 +31,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(built):
     dll = ctypes.CDLL(built)
     want = header_symbols()
-    assert len(want) == 8 + 3 * 31 + 6
+    assert len(want) == 8 + 5 * 32 + 6
     for s in sorted(want):
         assert hasattr(dll, s), s
     assert want == set(mlib.exported_symbols())
@@ -39,7 +40,9 @@ def test_library_exports_every_declared_symbol(built):
 def test_loader_binds_and_reports(built):
     l = mlib.load()
     assert b"sm_100a" in l.mab_version()
-    assert mlib.params("X25519") == {"wordlength": 32, "nlimbs": 8, "radix": 32, "nbits": 255, "nbytes": 32}
+    q = mlib.params("X25519")
+    assert (q["wordlength"], q["nlimbs"], q["radix"], q["nbits"], q["nbytes"]) == (32, 8, 32, 255, 32)
+    assert mlib.params("SECP256K1")["montgomery"] == 1 and mlib.params("NIST256ORDER")["pm1d2"] == 4
     assert mlib.params("X448")["nlimbs"] == 14 and mlib.params("NIST256")["nbytes"] == 32
     # SURVEY.md 8d work counts with this build's chains (251S+13M, 445S+14M)
     assert mlib.products("X25519", "modmul") == 64 and mlib.products("X25519", "modsqr") == 36

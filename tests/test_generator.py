@@ -4,8 +4,8 @@ import random
 
 import pytest
 
-from modarith_b200.primes import PRIMES
-from modarith_b200.gen.plan import make_plan, PseudoMersenne, GenMersenne, Montgomery, words, value
+from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime
+from modarith_b200.gen.plan import make_plan, PseudoMersenne, GenMersenne, Montgomery, MontgomeryFull, words, value
 from modarith_b200.gen.ptx import Asm, LostCarry
 from modarith_b200.gen import satmul
 from modarith_b200.gen.emit import emit_field_header
@@ -35,6 +35,9 @@ def test_product_counts(name):
     b = plan.build()
     L = plan.L
     fold = L if name == "X25519" else 0
+    if isinstance(plan, MontgomeryFull):      # separated-operand REDC: + L(L+1)/2 - L (low half) + L^2 (Q*p)
+        assert b["mul"].stats()[0] <= L * L + L * (L + 1) // 2 + L * L
+        return
     assert b["mul"].stats()[0] == L * L + fold
     assert b["sqr"].stats()[0] == L * (L + 1) // 2 + fold
     assert b["add"].stats()[0] == 0 and b["sub"].stats()[0] == 0
@@ -84,3 +87,18 @@ def test_emitted_header_is_reproducible(name):
     path = os.path.join(ROOT, "modarith_b200", "csrc", "gen", "field_%s.cuh" % name)
     assert open(path).read() == text
     assert "asm(" in text and "MAB_HOSTSIM" in text and "madc.hi.cc.u32" in text
+
+
+def test_fallback_plan_accepts_any_odd_modulus():
+    """Every kind of prime the reference's named tables hold gets a plan that passes the bignum
+    self-check: odd limb counts, unshaped Montgomery moduli, group orders (monty.py:1961-2127)."""
+    assert isinstance(make_plan(PRIMES["SECP256K1"]), MontgomeryFull)
+    assert isinstance(make_plan(PRIMES["NIST256ORDER"]), MontgomeryFull)
+    for nm, p in {"NIST384": 2**384 - 2**128 - 2**96 + 2**32 - 1, "NIST521": 2**521 - 1, "PM266": 2**266 - 3,
+                  "NIST224": 2**224 - 2**96 + 1, "GM480": 2**480 - 2**240 - 1,
+                  "ED25519ORDER": 2**252 + 27742317777372353535851937790883648493}.items():
+        plan = make_plan(Prime(nm, p, "monty"))
+        assert plan.self_check(trials=40, seed=7)
+    for nm, p in {"PM383": 2**383 - 187, "PM512": 2**512 - 569}.items():
+        plan = make_plan(Prime(nm, p, "pseudo"))
+        assert isinstance(plan, PseudoMersenne) and plan.self_check(trials=40, seed=7)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from field_oracle import FieldOracle, rfc7748
-from modarith_b200.primes import PRIMES
+from modarith_b200.primes import ALL_PRIMES as PRIMES
 import util
 
 CURVES = ("X25519", "X448")
@@ -124,7 +124,7 @@ def test_every_api_function_vs_oracle(hostsim, name):
     for r in (0, 1, 31, 32, 100, F.P.nbits - 1, 8 * F.nbytes - 1, 8 * F.nbytes, 8 * F.nbytes + 5):
         assert S.exp(S.raw("2R", scalar=r)[0]) == F.mod2r(r)
     # modshr is defined on the canonical STORED value (plain value for the non-Montgomery moduli)
-    if name != "NIST256":
+    if name in ("X25519", "X448"):
         for x in vals:
             r, out, _ = S.raw("SHR", S.imp(x)[0], scalar=8)
             assert (S.exp(r), out) == F.modshr(8, x)

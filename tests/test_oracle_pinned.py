@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from field_oracle import FieldOracle, rfc7748
-from modarith_b200.primes import PRIMES
+from modarith_b200.primes import PRIMES, ALL_PRIMES
 from modarith_b200 import addchain
 import util
 
@@ -73,7 +73,7 @@ def test_rfc7748_validation_tail(golden_rfc, curve):
         assert rfc7748(curve, bytes.fromhex(r["k"]), bytes.fromhex(r["u"]), twist_secure=False).hex() == r["out"], r
 
 
-@pytest.mark.parametrize("name", list(PRIMES))
+@pytest.mark.parametrize("name", list(ALL_PRIMES))
 def test_field_golden(golden_field, name):
     """Field-level vectors produced by the reference's generated 64-bit C (tests/golden/make_golden.py)."""
     g = golden_field[name]
@@ -176,7 +176,8 @@ def test_oracle_against_reference_build(ref_libs):
         out = util.ref_rfc7748_batch(ref_libs[c], k, u)
         for i in range(48):
             assert rfc7748(c, k[i].tobytes(), u[i].tobytes()) == out[i].tobytes()
-    for name, key in (("X25519", "X25519_generic"), ("X448", "X448_generic"), ("NIST256", "NIST256")):
+    for name, key in (("X25519", "X25519_generic"), ("X448", "X448_generic"), ("NIST256", "NIST256"),
+                      ("SECP256K1", "SECP256K1"), ("NIST256ORDER", "NIST256ORDER")):
         if key not in ref_libs:
             continue
         F = FieldOracle(name)

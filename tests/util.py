@@ -4,7 +4,7 @@ import ctypes
 import numpy as np
 
 from field_oracle import FieldOracle, rfc7748 as oracle_rfc7748  # noqa: F401
-from modarith_b200.primes import PRIMES
+from modarith_b200.primes import ALL_PRIMES as PRIMES
 
 SIM_OPS = ["ADD", "SUB", "NEG", "MUL", "SQR", "MLI", "NSQR", "PRO", "INV", "INVH", "QR", "QRH", "SQRT", "SQRTH",
            "IS1", "IS0", "ONE", "INT", "NRES", "REDC", "CSW", "CMV", "SHL", "SHR", "HAF", "2R", "SIGN", "CMP", "FSB",

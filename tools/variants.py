@@ -57,7 +57,7 @@ def build_variant(spec):
         if p.wait() != 0:
             raise SystemExit("nvcc failed for %s %s:\n%s" % (tag, unit, open(obj + ".log").read()[-3000:]))
     lib = os.path.join(d, "libmodarith_b200.so")
-    subprocess.check_call([b._nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    subprocess.check_call([b._nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
     regs = {}
     for line in open(os.path.join(d, "mab_capi_X25519.o.log")):
         if "Compiling entry function" in line:
