@@ -102,7 +102,7 @@ def cpu_baseline(sample_keys):
     rate = k.shape[0] / dt
     n = sample_keys if sample_keys > 0 else 0
     if n == 0:
-        n = int(max(8192, min(1 << 20, rate * 3.0)))      # ~3 s wall on all cores = ~3*cores CPU-seconds
+        n = int(max(8192, min(1 << 20, rate * 1.5)))      # ~1.5 s wall on all cores (about 25-50 CPU-seconds)
     k, u = make_inputs(n, 7748)
     dt, _ = time_reference(lib, k, u, cores)
     return {"value": n / dt, "unit": "scalar-mults/s", "cores": cores, "kind": "reference",
@@ -253,6 +253,19 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
         t = _time(lambda: F.modsqrt(xs, None, rs), 2)
         ps = mlib.products(name, "modsqrt")
         res["modsqrt"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": ps, "imad_frac": (m / t * ps / pk) if pk else None}
+        if name == "X25519":
+            # the reference's own WL=32 limb plan (radix 2^29 x 9, csrc/mab_unsat29.cuh) on the same chain
+            ua = torch.randint(0, 1 << 29, (9, m), dtype=torch.int32, device=dev, generator=gen)
+            ub = torch.randint(0, 1 << 29, (9, m), dtype=torch.int32, device=dev, generator=gen)
+            uc = torch.empty_like(ua)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            t = _time(lambda: mlib.check(lib.mab_probe_unsat29_modmul(ua.data_ptr(), ub.data_ptr(), uc.data_ptr(),
+                                                                      iters, m, m, st)), 2)
+            res["modmul_register_resident_unsaturated_9x29"] = {
+                "value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
+                "imad_frac": (m * iters / t * L * L / pk) if pk else None,
+                "note": "comparison kernel on the reference's radix-2^29 x 9 limb plan; same algorithmic 64 products"}
+            del ua, ub, uc
         out[name] = res
         del x, y, r, xs, ys, rs
     return out

@@ -72,6 +72,12 @@ MAB_API int mab_imad_peak(int variant, int iters, int blocks, int threads, float
 MAB_API int mab_pipe_probe(int variant, int iters, int blocks, int threads, float *ms, const char **name,
                            int *nwide, int *nalu, void *stream);
 
+/* Comparison kernel (csrc/mab_unsat29.cuh), not on the product path: c = a * b^iters mod 2^255-19 on the
+ * REFERENCE's WL=32 limb plan (unsaturated radix 2^29, 9 limb planes, pseudo.py:124-140), so that the
+ * choice of saturated limbs is backed by a measurement.  Limbs in, limbs out (value = sum c[k]*2^(29k)). */
+MAB_API int mab_probe_unsat29_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, unsigned int iters,
+                                     size_t n, size_t stride, void *stream);
+
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
   /* macros of the generated header (pseudo.py:1403-1407) plus the modpro chain cost; any pointer may be NULL */ \

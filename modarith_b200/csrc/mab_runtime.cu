@@ -11,6 +11,7 @@
 #include "gen/field_NIST256.cuh"
 #include "mab_probe.cuh"
 #include "mab_workspace.h"
+#include "mab_unsat29.cuh"
 #include <mutex>
 
 // ------------------------------------------------------------------------------------------
@@ -240,6 +241,13 @@ int mab_imad_peak(int variant, int iters, int blocks, int threads, float* ms, do
   cudaEventDestroy(t1);
   cudaFree(d);
   return (int)e;
+}
+
+int mab_probe_unsat29_modmul(const uint32_t* a, const uint32_t* b, uint32_t* c, unsigned int iters, size_t n, size_t stride, void* stream) {
+  if (n == 0) return 0;
+  if (stride < n) return MAB_ERR_BADARG;
+  k_unsat29_mulchain<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, b, c, iters, n, stride);
+  return (int)cudaGetLastError();
 }
 
 int mab_pipe_probe(int variant, int iters, int blocks, int threads, float* ms, const char** name, int* nwide, int* nalu, void* stream) {

@@ -83,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.mab_imad_peak.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_double), c_void_p]
     lib.mab_pipe_probe.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_char_p), POINTER(c_int),
                                    POINTER(c_int), c_void_p]
+    lib.mab_probe_unsat29_modmul.argtypes = [_P, _P, _P, c_uint, c_size_t, c_size_t, c_void_p]
     for P in PRIMES:
         for name, lead in FIELD_SIGNATURES.items():
             fn = getattr(lib, "mab_%s_%s" % (P, name))
@@ -105,7 +106,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     """Every symbol include/modarith_b200.h declares (used by the CPU-side ABI test)."""
     syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak",
-            "mab_pipe_probe", "mab_release_workspaces"]
+            "mab_pipe_probe", "mab_release_workspaces", "mab_probe_unsat29_modmul"]
     for P in PRIMES:
         syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
     for P in CURVES:

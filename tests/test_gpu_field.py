@@ -217,3 +217,31 @@ def test_p256_full_size_properties():
     F.modmul(x, y, r)
     F.modmul(y, x, s)
     assert int(F.modcmp(r, s).sum()) == n
+
+
+def test_unsaturated_comparison_kernel():
+    """csrc/mab_unsat29.cuh (the reference's radix-2^29 x 9 plan, kept only to be measured against the
+    saturated plan) computes a * b^k mod 2^255-19."""
+    from modarith_b200 import lib as mlib
+    l = mlib.load()
+    p = PRIMES["X25519"].p
+    rng = random.Random(29)
+    n, iters = 300, 37
+    xs, ys = [rng.randrange(p) for _ in range(n)], [rng.randrange(p) for _ in range(n)]
+
+    def planes(vals):
+        a = np.zeros((9, n), dtype=np.uint32)
+        for i, v in enumerate(vals):
+            for k in range(9):
+                a[k, i] = (v >> (29 * k)) & ((1 << 29) - 1)
+        return torch.from_numpy(a.view(np.int32)).cuda()
+
+    a, b = planes(xs), planes(ys)
+    c = torch.empty_like(a)
+    mlib.check(l.mab_probe_unsat29_modmul(a.data_ptr(), b.data_ptr(), c.data_ptr(), iters, n, n,
+                                          torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out = c.cpu().numpy().view(np.uint32).astype(object)
+    for i in range(n):
+        got = sum(int(out[k, i]) << (29 * k) for k in range(9)) % p
+        assert got == xs[i] * pow(ys[i], iters, p) % p
