@@ -152,6 +152,10 @@ MAB_DECLARE_FIELD(NIST256ORDER)
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */
 MAB_API int mab_X25519_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
 MAB_API int mab_X448_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
+/* Same results from the plain kernel (one key per thread, one inversion per key); the default entry
+ * points above share one inversion among up to four keys per thread.  Kept for comparison. */
+MAB_API int mab_X25519_rfc7748_perkey(const char *bk, const char *bu, char *bv, size_t n, void *stream);
+MAB_API int mab_X448_rfc7748_perkey(const char *bk, const char *bu, char *bv, size_t n, void *stream);
 /* The same driver compiled WITHOUT `#define TWIST_SECURE` (rfc7748.c:228-251): cheap point validation
  * (eprint 2020/1497); bv[i] is all zero when bu[i] is not the x-coordinate of a point on the curve. */
 MAB_API int mab_X25519_rfc7748_validate(const char *bk, const char *bu, char *bv, size_t n, void *stream);

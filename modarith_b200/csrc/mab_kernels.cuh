@@ -222,3 +222,50 @@ template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k
   }
   aos_st<L>(bv, i, align, out);
 }
+
+// rfc7748 with the inversions of up to four keys per thread shared (Rfc7748<F>::finish_batch).
+// Persistent grid (one launch fills the GPU exactly): warps advance in ROUNDS; in a round every warp
+// owns 32*K consecutive keys and every thread runs K ladders back to back (K = 4 while at least four
+// full rounds of keys remain, then 2, then 1), so all warps do identical work with no atomics and the
+// tail never costs more than one K=1 round.
+#define MAB_LADDER_KMAX 4
+template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
+  constexpr int L = F::L;
+  constexpr int T = MAB_LADDER_THREADS;
+  extern __shared__ uint32_t mab_smem[];
+  uint32_t* st = mab_smem + threadIdx.x;                               // K slots x 3 elements x L words
+  uint32_t* stash = F::LADDER_STASH ? (mab_smem + MAB_LADDER_KMAX * 3 * L * T + threadIdx.x) : nullptr;
+  const size_t per_round = (size_t)gridDim.x * T;                      // keys per round at K = 1
+  const size_t gw = (size_t)blockIdx.x * (T / 32) + (threadIdx.x >> 5);
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t base = 0; base < n;) {
+    const size_t rem = n - base;
+    const int K = (rem >= 4 * per_round) ? 4 : (rem >= 2 * per_round) ? 2 : 1;
+    MAB_NOUNROLL
+    for (int j = 0; j < K; j++) {
+      const size_t idx = base + (gw * K + j) * 32 + lane;
+      uint32_t k[L], u[L], x1[L], x2[L], z2[L];
+      if (idx < n) {
+        aos_ld<L>(k, bk, idx, align);
+        aos_ld<L>(u, bu, idx, align);
+      } else {
+#pragma unroll
+        for (int w = 0; w < L; w++) { k[w] = 0; u[w] = 0; }
+      }
+      Rfc7748<F>::ladder(x2, z2, x1, k, u, stash, T);
+      Rfc7748<F>::st_(st, T, j, 0, x2);
+      Rfc7748<F>::st_(st, T, j, 1, z2);
+    }
+    Rfc7748<F>::finish_batch(st, T, K);
+    MAB_NOUNROLL
+    for (int j = 0; j < K; j++) {
+      const size_t idx = base + (gw * K + j) * 32 + lane;
+      if (idx < n) {
+        uint32_t out[L];
+        Rfc7748<F>::ld(out, st, T, j, 0);
+        aos_st<L>(bv, idx, align, out);
+      }
+    }
+    base += per_round * K;
+  }
+}

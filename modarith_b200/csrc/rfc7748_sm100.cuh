@@ -33,12 +33,21 @@ template <class F> struct Rfc7748 {
   template <bool VALIDATE = false>
   static MAB_DEV void scalarmult(uint32_t (&out)[L], uint32_t (&k)[L], uint32_t (&u)[L],
                                  uint32_t* stash = nullptr, int pitch = 0) {
+    uint32_t x1[L], x2[L], z2[L];
+    ladder(x2, z2, x1, k, u, stash, pitch);
+    tail<VALIDATE>(out, x2, z2, x1, stash, pitch);
+  }
+
+  // clamp, import, and the Nbits ladder steps (rfc7748.c:166-223): leaves the projective result
+  // (x2 : z2) and x1 = u in internal form (x1 also in the stash when one is given).
+  static MAB_DEV void ladder(uint32_t (&x2)[L], uint32_t (&z2)[L], uint32_t (&x1)[L], uint32_t (&k)[L],
+                             uint32_t (&u)[L], uint32_t* stash = nullptr, int pitch = 0) {
     // mask() (rfc7748.c:148-152,172): drop the bits above Nbits in the top byte of u
     constexpr int rbits = (F::NBITS % 8) ? (F::NBITS % 8) : 8;
     u[L - 1] &= ((((1u << rbits) - 1u) << 24) | 0x00ffffffu);
     clamp(k);
 
-    uint32_t x1[L], x2[L], z2[L], x3[L], z3[L];
+    uint32_t x3[L], z3[L];
     (void)Fd::from_words(x1, u);                 // modimp (rfc7748.c:178)
     Fd::one(x2);
     Fd::zer(z2);
@@ -102,7 +111,12 @@ template <class F> struct Rfc7748 {
     }
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);
+  }
 
+  // the part after the ladder (rfc7748.c:225-255): x2/z2 (0 -> 0), canonical little-endian words
+  template <bool VALIDATE>
+  static MAB_DEV void tail(uint32_t (&out)[L], uint32_t (&x2)[L], uint32_t (&z2)[L], const uint32_t (&x1)[L],
+                           uint32_t* stash, int pitch) {
     if (!VALIDATE) {
       // TWIST_SECURE branch (rfc7748.c:225-227,252): x2/z2 with 0 -> 0
       uint32_t h[L];
@@ -141,5 +155,60 @@ template <class F> struct Rfc7748 {
     }
     F::mul(x2, x2, z2);
     Fd::to_words(out, x2);                       // modexp (rfc7748.c:254)
+  }
+
+  // ---- one inversion for K keys (Montgomery's simultaneous-inversion trick) ---------------------------
+  // A thread that has run K ladders back to back finishes them together: the K progenitor chains of
+  // rfc7748.c:226-227 (each ~Nbits squarings, a tenth of a scalar multiplication) become ONE chain plus
+  // 3(K-1) multiplications.  Results are identical: x2_j * z2_j^-1 is what every key gets, and a key
+  // whose z2 is zero (low-order input) still gives zero as modinv(0)=0 does (pseudo.py:788-812): its z2
+  // is replaced by 1 inside the product and its result forced to zero, all branch-free.
+  // st: this thread's column of K slots x 3 elements x L words; element e of slot j, word w at
+  // st[((j*3+e)*L + w)*pitch].  In: e0 = x2, e1 = z2.  Out: e0 = canonical result words.
+  static MAB_DEV void finish_batch(uint32_t* st, int pitch, int K) {
+    uint32_t acc[L], z[L], t[L], one[L];
+    Fd::one(one);
+    uint32_t flags = 0;
+    MAB_NOUNROLL
+    for (int j = 0; j < K; j++) {
+      ld(z, st, pitch, j, 1);
+      uint32_t f = Fd::is0(z);
+      flags |= f << j;
+      Fd::cmv(f, one, z);                        // z' = 1 where z2 == 0
+      st_(st, pitch, j, 1, z);
+      if (j == 0) Fd::cpy(acc, z); else F::mul(acc, acc, z);
+      st_(st, pitch, j, 2, acc);                 // prefix product P_j
+    }
+    {
+      uint32_t h[L];
+      F::pro(h, acc);
+      Fd::template inv<true>(acc, acc, h);       // 1 / (z'_0 ... z'_{K-1})
+    }
+    MAB_NOUNROLL
+    for (int j = K - 1; j >= 0; j--) {
+      if (j > 0) {
+        ld(t, st, pitch, j - 1, 2);
+        F::mul(t, acc, t);                       // 1 / z'_j
+        ld(z, st, pitch, j, 1);
+        F::mul(acc, acc, z);                     // 1 / (z'_0 ... z'_{j-1})
+      } else {
+        Fd::cpy(t, acc);
+      }
+      ld(z, st, pitch, j, 0);
+      F::mul(z, z, t);                           // x2_j / z2_j
+      uint32_t zero[L];
+      Fd::zer(zero);
+      Fd::cmv((flags >> j) & 1u, zero, z);
+      Fd::to_words(t, z);
+      st_(st, pitch, j, 0, t);
+    }
+  }
+  static MAB_DEV void ld(uint32_t (&r)[L], const uint32_t* st, int pitch, int j, int e) {
+#pragma unroll
+    for (int w = 0; w < L; w++) r[w] = st[((j * 3 + e) * L + w) * pitch];
+  }
+  static MAB_DEV void st_(uint32_t* st, int pitch, int j, int e, const uint32_t (&r)[L]) {
+#pragma unroll
+    for (int w = 0; w < L; w++) st[((j * 3 + e) * L + w) * pitch] = r[w];
   }
 };

@@ -93,6 +93,9 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, "mab_%s_rfc7748" % P)
         fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
         fn.restype = c_int
+        fn = getattr(lib, "mab_%s_rfc7748_perkey" % P)
+        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
+        fn.restype = c_int
         fn = getattr(lib, "mab_%s_rfc7748_validate" % P)
         fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
         fn.restype = c_int
@@ -110,7 +113,8 @@ def exported_symbols():
     for P in PRIMES:
         syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
     for P in CURVES:
-        syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_validate" % P]
+        syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_validate" % P,
+                 "mab_%s_rfc7748_perkey" % P]
     return syms
 
 

@@ -78,7 +78,30 @@ template <class F, bool VALIDATE = false> static void sim_rfc7748(const unsigned
   memcpy(bv, out, 4 * L);
 }
 
+// K keys through one simulated thread: K ladders, then Rfc7748<F>::finish_batch (one shared inversion)
+template <class F> static void sim_rfc7748_shared_inversion(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) {
+  constexpr int L = F::L;
+  uint32_t st[4 * 3 * L];
+  uint32_t stash[2 * L];
+  for (int j = 0; j < K; j++) {
+    uint32_t k[L], u[L], x1[L], x2[L], z2[L];
+    memcpy(k, bk + 4 * L * j, 4 * L);
+    memcpy(u, bu + 4 * L * j, 4 * L);
+    Rfc7748<F>::ladder(x2, z2, x1, k, u, F::LADDER_STASH ? stash : nullptr, 1);
+    Rfc7748<F>::st_(st, 1, j, 0, x2);
+    Rfc7748<F>::st_(st, 1, j, 1, z2);
+  }
+  Rfc7748<F>::finish_batch(st, 1, K);
+  for (int j = 0; j < K; j++) {
+    uint32_t out[L];
+    Rfc7748<F>::ld(out, st, 1, j, 0);
+    memcpy(bv + 4 * L * j, out, 4 * L);
+  }
+}
+
 extern "C" {
+void sim_X25519_rfc7748_shared(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) { sim_rfc7748_shared_inversion<F_X25519>(bk, bu, bv, K); }
+void sim_X448_rfc7748_shared(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) { sim_rfc7748_shared_inversion<F_X448>(bk, bu, bv, K); }
 int sim_X25519_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X25519>(op, a, b, s, r, r2); }
 int sim_X448_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X448>(op, a, b, s, r, r2); }
 int sim_NIST256_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_NIST256>(op, a, b, s, r, r2); }

@@ -24,14 +24,14 @@ def header_symbols():
     for P in re.findall(r"MAB_DECLARE_FIELD\((\w+)\)\n", h):
         if P != "P":
             syms |= {"mab_%s_%s" % (P, m) for m in macro}
-    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host|_validate)?)\s*\(", h))
+    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host|_validate|_perkey)?)\s*\(", h))
     return syms
 
 
 def test_library_exports_every_declared_symbol(built):
     dll = ctypes.CDLL(built)
     want = header_symbols()
-    assert len(want) == 9 + 5 * 32 + 6
+    assert len(want) == 9 + 5 * 32 + 8
     for s in sorted(want):
         assert hasattr(dll, s), s
     assert want == set(mlib.exported_symbols())

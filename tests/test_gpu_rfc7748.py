@@ -60,6 +60,33 @@ def test_validation_tail(golden_rfc, ref_libs, curve):
         assert np.array_equal(out, util.ref_rfc7748_batch(ref_libs[key], k, u))
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_shared_inversion_rounds_vs_one_inversion_per_key(curve):
+    """The default kernel (persistent rounds, up to four keys per thread share one inversion) against the
+    plain one-key-per-thread kernel, on batch sizes that exercise K = 4, 2 and 1 rounds with ragged tails,
+    with low-order inputs (zero results) scattered through the batch."""
+    from modarith_b200 import lib as mlib
+    l = mlib.load()
+    nb = PRIMES[curve].nbytes
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    per_round = sms * (4 if curve == "X25519" else 2) * 128
+    for n in (1, 31, per_round - 1, 2 * per_round + 5, 4 * per_round + 1000, 7 * per_round + 33):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        k = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
+        u = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
+        u[::97] = 0                          # u = 0 -> z2 = 0 -> all-zero output
+        if n > 5:
+            u[5] = 0
+            u[5, 0] = 1                      # u = 1: another low-order point
+        a, b = torch.empty_like(k), torch.empty_like(k)
+        st = torch.cuda.current_stream().cuda_stream
+        mlib.check(getattr(l, "mab_%s_rfc7748" % curve)(k.data_ptr(), u.data_ptr(), a.data_ptr(), n, st))
+        mlib.check(getattr(l, "mab_%s_rfc7748_perkey" % curve)(k.data_ptr(), u.data_ptr(), b.data_ptr(), n, st))
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), (curve, n)
+        assert int((a[::97] != 0).sum()) == 0
+
+
 def test_demo_loop_x25519(golden_rfc):
     """rfc7748.c:main: 5000 x 2 chained calls, each output feeding the next."""
     from modarith_b200.rfc7748 import rfc7748

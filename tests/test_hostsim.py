@@ -40,6 +40,33 @@ def test_ladder_validation_tail(hostsim, golden_rfc, curve):
         assert out.raw[:nb].hex() == r["out"], r
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_shared_inversion(hostsim, golden_rfc, curve):
+    """K ladders finished with ONE inversion (Rfc7748<F>::finish_batch): same bytes as one inversion per
+    key, including keys whose z2 is zero (low-order inputs: u = 0, 1, p-1 ...) mixed into the batch."""
+    nb = golden_rfc[curve]["nbytes"]
+    fn = getattr(hostsim, "sim_%s_rfc7748_shared" % curve)
+    rows = golden_rfc[curve]["edge"] + golden_rfc[curve]["random"][:13]
+    zero_rows = [r for r in rows if int(r["out"], 16) == 0]
+    assert zero_rows, "the edge set must contain low-order inputs"
+    rng = random.Random(4)
+    for K in (1, 2, 3, 4):
+        for _ in range(6):
+            pick = rng.sample(rows, K)
+            if K > 1:
+                pick[rng.randrange(K)] = rng.choice(zero_rows)
+            k = b"".join(bytes.fromhex(r["k"]) for r in pick)
+            u = b"".join(bytes.fromhex(r["u"]) for r in pick)
+            out = ctypes.create_string_buffer(nb * K)
+            fn(k, u, out, K)
+            assert [out.raw[nb * j:nb * (j + 1)].hex() for j in range(K)] == [r["out"] for r in pick], (curve, K)
+    # all keys zero
+    pick = [zero_rows[0]] * 4
+    out = ctypes.create_string_buffer(nb * 4)
+    fn(b"".join(bytes.fromhex(r["k"]) for r in pick), b"".join(bytes.fromhex(r["u"]) for r in pick), out, 4)
+    assert out.raw[:nb * 4] == bytes(nb * 4)
+
+
 def test_ladder_demo_loop(hostsim, golden_rfc):
     """rfc7748.c:main's 5000x2 chained loop (X25519): every output feeds the next call."""
     d = golden_rfc["X25519"]["demo"]
