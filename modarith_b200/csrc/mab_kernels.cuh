@@ -224,26 +224,36 @@ template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k
 }
 
 // rfc7748 with the inversions of up to four keys per thread shared (Rfc7748<F>::finish_batch).
-// Persistent grid (one launch fills the GPU exactly): warps advance in ROUNDS; in a round every warp
-// owns 32*K consecutive keys and every thread runs K ladders back to back (K = 4 while at least four
-// full rounds of keys remain, then 2, then 1), so all warps do identical work with no atomics and the
-// tail never costs more than one K=1 round.
+// Persistent grid (one launch fills the GPU exactly); each warp repeatedly takes the next CHUNK of
+// 32*K consecutive keys from an atomic counter and every thread runs K ladders back to back before one
+// shared inversion.  The chunk list is fixed by the host: K = 4 chunks first, then K = 2, then K = 1, the
+// small ones last so that warps the scheduler favoured (they run ahead: the sub-partition arbiter is not
+// fair) pick up more of them and all warps finish together.
 #define MAB_LADDER_KMAX 4
-template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align) {
+struct MabChunks {
+  unsigned long long* counter;     // zeroed before the launch
+  unsigned c4, c2;                 // number of K=4 chunks, then of K=2 chunks; K=1 chunks follow up to n
+};
+template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align, MabChunks ch) {
   constexpr int L = F::L;
   constexpr int T = MAB_LADDER_THREADS;
   extern __shared__ uint32_t mab_smem[];
   uint32_t* st = mab_smem + threadIdx.x;                               // K slots x 3 elements x L words
   uint32_t* stash = F::LADDER_STASH ? (mab_smem + MAB_LADDER_KMAX * 3 * L * T + threadIdx.x) : nullptr;
-  const size_t per_round = (size_t)gridDim.x * T;                      // keys per round at K = 1
-  const size_t gw = (size_t)blockIdx.x * (T / 32) + (threadIdx.x >> 5);
   const unsigned lane = threadIdx.x & 31;
-  for (size_t base = 0; base < n;) {
-    const size_t rem = n - base;
-    const int K = (rem >= 4 * per_round) ? 4 : (rem >= 2 * per_round) ? 2 : 1;
+  for (;;) {
+    unsigned long long ci = 0;
+    if (lane == 0) ci = atomicAdd(ch.counter, 1ULL);
+    ci = __shfl_sync(0xffffffffu, ci, 0);
+    int K;
+    size_t start;
+    if (ci < ch.c4) { K = 4; start = (size_t)ci * 128; }
+    else if (ci < (unsigned long long)ch.c4 + ch.c2) { K = 2; start = (size_t)ch.c4 * 128 + (size_t)(ci - ch.c4) * 64; }
+    else { K = 1; start = (size_t)ch.c4 * 128 + (size_t)ch.c2 * 64 + (size_t)(ci - ch.c4 - ch.c2) * 32; }
+    if (start >= n) break;
     MAB_NOUNROLL
     for (int j = 0; j < K; j++) {
-      const size_t idx = base + (gw * K + j) * 32 + lane;
+      const size_t idx = start + (size_t)j * 32 + lane;
       uint32_t k[L], u[L], x1[L], x2[L], z2[L];
       if (idx < n) {
         aos_ld<L>(k, bk, idx, align);
@@ -259,13 +269,12 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
     Rfc7748<F>::finish_batch(st, T, K);
     MAB_NOUNROLL
     for (int j = 0; j < K; j++) {
-      const size_t idx = base + (gw * K + j) * 32 + lane;
+      const size_t idx = start + (size_t)j * 32 + lane;
       if (idx < n) {
         uint32_t out[L];
         Rfc7748<F>::ld(out, st, T, j, 0);
         aos_st<L>(bv, idx, align, out);
       }
     }
-    base += per_round * K;
   }
 }

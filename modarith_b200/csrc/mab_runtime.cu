@@ -120,6 +120,30 @@ int mab_host_workspace_acquire(int device, size_t bytes, MabWorkspace** out) {
 
 void mab_host_workspace_release(MabWorkspace* ws) { g_ws_mutex[ws->device].unlock(); }
 
+// ---- work counters of the persistent ladder kernels --------------------------------------------------
+#define MAB_NCOUNTERS 1024
+static unsigned long long* g_counters[MAB_WS_MAXDEV];
+static unsigned g_counter_next[MAB_WS_MAXDEV];
+static std::mutex g_counter_mutex;
+
+int mab_chunk_counter(cudaStream_t stream, unsigned long long** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= MAB_WS_MAXDEV) return MAB_ERR_BADARG;
+  unsigned long long* slot;
+  {
+    std::lock_guard<std::mutex> g(g_counter_mutex);
+    if (!g_counters[dev]) {
+      if ((e = cudaMalloc((void**)&g_counters[dev], MAB_NCOUNTERS * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+    }
+    slot = g_counters[dev] + (g_counter_next[dev]++ % MAB_NCOUNTERS);
+  }
+  if ((e = cudaMemsetAsync(slot, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return (int)e;
+  *out = slot;
+  return 0;
+}
+
 static const char* kVersion = "modarith_b200 0.1 (sm_100a)";
 
 // W(modmul)=L^2, W(modsqr)=L(L+1)/2, W(modmli)=L with L=ceil(Nbits/32); chains

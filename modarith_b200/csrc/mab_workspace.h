@@ -14,3 +14,7 @@ struct MabWorkspace {
 // Locks the device's workspace, growing each of its three buffers to at least `bytes`.
 int mab_host_workspace_acquire(int device, size_t bytes, MabWorkspace** out);
 void mab_host_workspace_release(MabWorkspace* ws);
+// A zeroed 64-bit work counter for one launch of a persistent kernel: slots of a small per-device pool
+// are handed out round-robin and cleared on `stream` ahead of the launch, so launches that overlap on
+// different streams never share one.
+int mab_chunk_counter(cudaStream_t stream, unsigned long long** out);
