@@ -396,8 +396,8 @@ def main():
         e2e_steps.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    per_chunk = 2 * props.multi_processor_count * 4 * 128          # mab_capi.inc: two waves of resident CTAs
-    chunks = (n_local + per_chunk - 1) // per_chunk
+    round_keys = props.multi_processor_count * 4 * 128             # mab_capi.inc: persistent grid, 4 CTAs/SM
+    chunks = max(1, (n_local + 5 * round_keys - 1) // (5 * round_keys))
     e2e_launches = args.steps * chunks
     if ref is not None and parity:
         _, want = time_reference(ref, hk[(args.steps - 1) % NSETS][:1024].numpy(), hu[(args.steps - 1) % NSETS][:1024].numpy(), 0)
