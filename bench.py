@@ -434,7 +434,10 @@ def main():
                 "products_per_key": prod,
                 "note": "achieved = keys/s/GPU x %d algorithmic 32x32->64 limb products per X25519 scalar-mult "
                         "(255 x (5M+4S+1 mli) + 251S+13M progenitor + inversion wrapper + final M, L=8); peak = "
-                        "IMAD-pipe products/s measured live by mab_imad_peak on this GPU" % prod}
+                        "IMAD-pipe products/s measured live by mab_imad_peak on this GPU.  The kernel shares one "
+                        "inversion among up to four keys per thread (Montgomery's trick), so it EXECUTES fewer products "
+                        "than this reference-algorithm count (about 9 700 fewer per key where sharing is four-way); the "
+                        "numerator is deliberately the reference's work per key, as SURVEY.md 8d defines it" % prod}
         if peak:
             roof["peak"] = peak["peak_products_per_s"] / 1e9
             roof["frac"] = achieved / peak["peak_products_per_s"]
