@@ -247,9 +247,15 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
         t = _time(lambda: F.modnsqr(rs, iters), 2)
         res["modsqr_register_resident"] = {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
                                            "imad_frac": (m * iters / t * (L * (L + 1) // 2) / pk) if pk else None}
-        t = _time(lambda: F.modinv(xs, None, rs), 2)
         pi = mlib.products(name, "modinv")
-        res["modinv"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": pi, "imad_frac": (m / t * pi / pk) if pk else None}
+        t = _time(lambda: F.modinv_perelement(xs, rs), 2)
+        res["modinv_one_chain_per_element"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": pi,
+                                               "imad_frac": (m / t * pi / pk) if pk else None}
+        t = _time(lambda: F.modinv(xs, None, rs), 2)
+        res["modinv"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": pi,
+                         "imad_frac_reference_work": (m / t * pi / pk) if pk else None,
+                         "note": "one progenitor chain shared by 8 elements per thread (Montgomery's trick): executes "
+                                 "about 1/6 of the reference algorithm's products, so this fraction can exceed 1"}
         t = _time(lambda: F.modsqrt(xs, None, rs), 2)
         ps = mlib.products(name, "modsqrt")
         res["modsqrt"] = {"value": m / t / 1e6, "unit": "Mop/s", "products": ps, "imad_frac": (m / t * ps / pk) if pk else None}

@@ -106,6 +106,8 @@ MAB_API int mab_probe_unsat29_modmul(const uint32_t *a, const uint32_t *b, uint3
   MAB_API int mab_##P##_modpro(const uint32_t *w, uint32_t *z, size_t n, size_t stride, void *stream);            \
   /* modinv   pseudo.py:788-812   h = progenitor planes or NULL; 0 -> 0 */                                \
   MAB_API int mab_##P##_modinv(const uint32_t *x, const uint32_t *h, uint32_t *z, size_t n, size_t stride, void *stream); \
+  /* modinv with one progenitor chain per element, as the reference spends it (modinv itself shares one chain among 8 elements when h == NULL) */ \
+  MAB_API int mab_##P##_modinv_perelement(const uint32_t *x, uint32_t *z, size_t n, size_t stride, void *stream); \
   /* modqr    pseudo.py:815-831   note (h, x) order; out[i] = 1 iff x is a QR or 0 */                     \
   MAB_API int mab_##P##_modqr(const uint32_t *h, const uint32_t *x, int *out, size_t n, size_t stride, void *stream); \
   /* modsqrt  pseudo.py:834-874 */                                                                        \

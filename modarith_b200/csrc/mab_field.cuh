@@ -67,6 +67,17 @@ template <class F> struct Field {
     return d == 0 ? 1u : 0u;
   }
 
+  // zero test on the STORED value (no redc: zero is zero in Montgomery form too); used where the
+  // value is only needed as a flag (shared inversions)
+  static MAB_DEV uint32_t is0_stored(const uint32_t (&a)[L]) {
+    uint32_t c[L];
+    (void)F::canon(c, a);
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) d |= c[i];
+    return d == 0 ? 1u : 0u;
+  }
+
   // modcsw / modcmv, mask form of pseudo.py:1006-1013,1041-1047 (PSCR=False): b in {0,1}
   static MAB_DEV void csw(uint32_t b, uint32_t (&g)[L], uint32_t (&f)[L]) {
     uint32_t m = 0u - b;

@@ -101,6 +101,50 @@ template <class F, int OP> __global__ void __launch_bounds__(128) k_field(MabArg
   plane_st<L>(p.r, p.stride, i, r);
 }
 
+// modinv (pseudo.py:788-812) over a batch with ONE progenitor chain per K elements: Montgomery's
+// simultaneous inversion inside each thread (K prefix products in registers, inputs re-read from HBM
+// on the way back -- 4L more bytes per element against ~(Nbits/K) fewer squarings).  Zero inputs are
+// replaced by one inside the product and give zero, as modinv(0) = 0 does; outputs may alias inputs.
+template <class F, int K> __global__ void __launch_bounds__(128) k_inv_shared(MabArgs p) {
+  constexpr int L = F::L;
+  typedef Field<F> Fd;
+  const size_t first = (size_t)blockIdx.x * K * blockDim.x + threadIdx.x;
+  uint32_t P[K][L], a[L], acc[L], one[L];
+  Fd::one(one);
+  uint32_t flags = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const size_t i = first + (size_t)j * blockDim.x;
+    if (i < p.n) plane_ld<L>(a, p.a, p.stride, i); else Fd::cpy(a, one);
+    const uint32_t f = Fd::is0_stored(a);
+    flags |= f << j;
+    Fd::cmv(f, one, a);
+    if (j == 0) Fd::cpy(P[0], a); else F::mul(P[j], P[j - 1], a);
+  }
+  {
+    uint32_t h[L];
+    F::pro(h, P[K - 1]);
+    Fd::template inv<true>(acc, P[K - 1], h);
+  }
+#pragma unroll
+  for (int j = K - 1; j >= 0; j--) {
+    const size_t i = first + (size_t)j * blockDim.x;
+    uint32_t r[L];
+    if (j > 0) {
+      if (i < p.n) plane_ld<L>(a, p.a, p.stride, i); else Fd::cpy(a, one);
+      Fd::cmv((flags >> j) & 1u, one, a);
+      F::mul(r, acc, P[j - 1]);
+      F::mul(acc, acc, a);
+    } else {
+      Fd::cpy(r, acc);
+    }
+    uint32_t zero[L];
+    Fd::zer(zero);
+    Fd::cmv((flags >> j) & 1u, zero, r);
+    if (i < p.n) plane_st<L>(p.r, p.stride, i, r);
+  }
+}
+
 // ---- byte strings ------------------------------------------------------------------
 // NW words of element i from an AoS byte array (element size 4*NW bytes), widest aligned access.
 template <int NW> static __device__ __forceinline__ void aos_ld(uint32_t (&w)[NW], const uint8_t* base, size_t i, unsigned align) {

@@ -68,7 +68,9 @@ template <class F> struct Rfc7748 {
     MAB_NOUNROLL
     for (int w = L - 1; w >= 0; w--) {           // rfc7748.c:186-221, bits Nbits-1 .. 0
       uint32_t kw = stash ? stash[w * pitch] : k[L - 1];
-      const int nb = (w == L - 1) ? topbits : 32;
+      // the lowest COF bits of a clamped scalar are zero (rfc7748.c:137): those steps are plain
+      // doublings of (x2:z2) and are done after the loop without the differential-addition half
+      const int nb = (w == L - 1) ? topbits : (w == 0 ? 32 - F::COF : 32);
       MAB_NOUNROLL
       for (int bi = 0; bi < nb; bi++) {
       uint32_t kt = kw >> 31;
@@ -111,6 +113,18 @@ template <class F> struct Rfc7748 {
     }
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);
+#pragma unroll 1
+    for (int i = 0; i < F::COF; i++) {           // bits COF-1..0 are 0: x2,z2 <- double(x2,z2)
+      uint32_t A[L], B[L];
+      F::add(A, x2, z2);
+      F::sub(B, x2, z2);
+      F::sqr(A, A);                              // AA
+      F::sqr(B, B);                              // BB
+      F::mul(x2, A, B);                          // x2 = AA*BB
+      F::sub(B, A, B);                           // E
+      F::mla(z2, B, F::A24, A);
+      F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
+    }
   }
 
   // the part after the ladder (rfc7748.c:225-255): x2/z2 (0 -> 0), canonical little-endian words
@@ -172,7 +186,7 @@ template <class F> struct Rfc7748 {
     MAB_NOUNROLL
     for (int j = 0; j < K; j++) {
       ld(z, st, pitch, j, 1);
-      uint32_t f = Fd::is0(z);
+      uint32_t f = Fd::is0_stored(z);
       flags |= f << j;
       Fd::cmv(f, one, z);                        // z' = 1 where z2 == 0
       st_(st, pitch, j, 1, z);

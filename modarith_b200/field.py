@@ -106,6 +106,10 @@ class Field:
     def modinv(self, x, h, z):
         self._call("modinv", [_ptr(x), _ptr(h), _ptr(z)], self._chk(x, h, z))
 
+    def modinv_perelement(self, x, z):
+        """modinv with one progenitor chain per element (comparison; `modinv` shares chains)"""
+        self._call("modinv_perelement", [_ptr(x), _ptr(z)], self._chk(x, z))
+
     def modqr(self, h, x):
         out = self._ints(x.shape[1])
         self._call("modqr", [_ptr(h), _ptr(x), _ptr(out)], self._chk(x, h))

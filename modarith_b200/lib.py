@@ -36,6 +36,7 @@ FIELD_SIGNATURES = {
     "modnsqr": [_P, c_int],
     "modpro": [_P, _P],
     "modinv": [_P, _P, _P],
+    "modinv_perelement": [_P, _P],
     "modqr": [_P, _P, _P],
     "modsqrt": [_P, _P, _P],
     "modis1": [_P, _P],

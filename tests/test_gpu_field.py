@@ -115,6 +115,30 @@ def test_every_api_function_vs_oracle(name):
 
 
 @pytest.mark.parametrize("name", NAMES)
+def test_shared_chain_modinv(name):
+    """modinv shares one progenitor chain among 8 elements per thread: same values as one chain per
+    element, zeros (and p, 2p-ish inputs that reduce to zero) anywhere in the batch, ragged sizes, in place."""
+    F = _field(name)
+    p = PRIMES[name].p
+    rng = random.Random(8)
+    for n in (1, 7, 129, 1024 + 3, 5000):
+        xs = [rng.randrange(p) for _ in range(n)]
+        for i in range(0, n, 11):
+            xs[i] = 0
+        if n > 3:
+            xs[3] = p                      # imports as zero
+        x = F.from_ints(xs)
+        want = [pow(v % p, -1, p) if v % p else 0 for v in xs]
+        z = F.alloc(n)
+        F.modinv(x, None, z)
+        assert F.to_ints(z) == want
+        F.modinv_perelement(x, z)
+        assert F.to_ints(z) == want
+        F.modinv(x, None, x)               # in place
+        assert F.to_ints(x) == want
+
+
+@pytest.mark.parametrize("name", NAMES)
 def test_aliasing_and_pitch(name):
     """Outputs may alias inputs (pseudo.py:1832-1845); planes may be a window of a wider pitch."""
     F = _field(name)
