@@ -9,6 +9,13 @@
 #pragma once
 #include "mab_field.cuh"
 
+// experiment switch: -DMAB_NO_TAIL_DOUBLING runs all Nbits steps through the full ladder step
+#ifdef MAB_NO_TAIL_DOUBLING
+#define MAB_TAIL_DOUBLINGS(F) 0
+#else
+#define MAB_TAIL_DOUBLINGS(F) (F::COF)
+#endif
+
 template <class F> struct Rfc7748 {
   static constexpr int L = F::L;
   typedef Field<F> Fd;
@@ -70,7 +77,7 @@ template <class F> struct Rfc7748 {
       uint32_t kw = stash ? stash[w * pitch] : k[L - 1];
       // the lowest COF bits of a clamped scalar are zero (rfc7748.c:137): those steps are plain
       // doublings of (x2:z2) and are done after the loop without the differential-addition half
-      const int nb = (w == L - 1) ? topbits : (w == 0 ? 32 - F::COF : 32);
+      const int nb = (w == L - 1) ? topbits : (w == 0 ? 32 - MAB_TAIL_DOUBLINGS(F) : 32);
       MAB_NOUNROLL
       for (int bi = 0; bi < nb; bi++) {
       uint32_t kt = kw >> 31;
@@ -114,7 +121,7 @@ template <class F> struct Rfc7748 {
     Fd::csw(swap, x2, x3);
     Fd::csw(swap, z2, z3);
 #pragma unroll 1
-    for (int i = 0; i < F::COF; i++) {           // bits COF-1..0 are 0: x2,z2 <- double(x2,z2)
+    for (int i = 0; i < MAB_TAIL_DOUBLINGS(F); i++) {   // bits COF-1..0 are 0: x2,z2 <- double(x2,z2)
       uint32_t A[L], B[L];
       F::add(A, x2, z2);
       F::sub(B, x2, z2);
