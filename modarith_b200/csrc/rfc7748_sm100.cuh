@@ -80,38 +80,38 @@ template <class F> struct Rfc7748 {
       const int nb = (w == L - 1) ? topbits : (w == 0 ? 32 - MAB_TAIL_DOUBLINGS(F) : 32);
       MAB_NOUNROLL
       for (int bi = 0; bi < nb; bi++) {
-      uint32_t kt = kw >> 31;
-      kw <<= 1;
-      swap ^= kt;
-      Fd::csw(swap, x2, x3);
-      Fd::csw(swap, z2, z3);
-      swap = kt;
+        uint32_t kt = kw >> 31;
+        kw <<= 1;
+        swap ^= kt;
+        Fd::csw(swap, x2, x3);
+        Fd::csw(swap, z2, z3);
+        swap = kt;
 
-      uint32_t A[L], B[L], C[L], D[L];
-      F::add(A, x2, z2);                         // A = x2+z2
-      F::sub(B, x2, z2);                         // B = x2-z2
-      F::add(C, x3, z3);                         // C = x3+z3
-      F::sub(D, x3, z3);                         // D = x3-z3
-      F::mul(D, D, A);                           // DA
-      F::mul(C, C, B);                           // CB
-      F::sqr(A, A);                              // AA
-      F::sqr(B, B);                              // BB
-      F::add(x3, D, C);
-      F::sub(z3, D, C);
-      F::sqr(x3, x3);                            // x3 = (DA+CB)^2
-      F::sqr(z3, z3);
-      if (stash) {
-        uint32_t t1[L];
+        uint32_t A[L], B[L], C[L], D[L];
+        F::add(A, x2, z2);                         // A = x2+z2
+        F::sub(B, x2, z2);                         // B = x2-z2
+        F::add(C, x3, z3);                         // C = x3+z3
+        F::sub(D, x3, z3);                         // D = x3-z3
+        F::mul(D, D, A);                           // DA
+        F::mul(C, C, B);                           // CB
+        F::sqr(A, A);                              // AA
+        F::sqr(B, B);                              // BB
+        F::add(x3, D, C);
+        F::sub(z3, D, C);
+        F::sqr(x3, x3);                            // x3 = (DA+CB)^2
+        F::sqr(z3, z3);
+        if (stash) {
+          uint32_t t1[L];
 #pragma unroll
-        for (int j = 0; j < L; j++) t1[j] = stash[(L + j) * pitch];
-        F::mul(z3, z3, t1);                      // z3 = x1*(DA-CB)^2
-      } else {
-        F::mul(z3, z3, x1);
-      }
-      F::mul(x2, A, B);                          // x2 = AA*BB
-      F::sub(B, A, B);                           // E = AA-BB
-      F::mla(z2, B, F::A24, A);                  // a24*E + AA  (modmli + modadd fused)
-      F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
+          for (int j = 0; j < L; j++) t1[j] = stash[(L + j) * pitch];
+          F::mul(z3, z3, t1);                      // z3 = x1*(DA-CB)^2
+        } else {
+          F::mul(z3, z3, x1);
+        }
+        F::mul(x2, A, B);                          // x2 = AA*BB
+        F::sub(B, A, B);                           // E = AA-BB
+        F::mla(z2, B, F::A24, A);                  // a24*E + AA  (modmli + modadd fused)
+        F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
       }
       if (!stash) {
 #pragma unroll
