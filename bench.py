@@ -222,6 +222,26 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
     out["x448"] = {"workload": "X448 ladder, 2^20 keys", "value": n / t, "unit": "scalar-mults/s",
                    "products_per_key": prod, "imad_frac": (n / t * prod / pk) if pk else None}
     del k, u, v
+    # P-256 scalar multiplication: ecnXXXset + ecnXXXmul + ecnXXXget, 2^18 points
+    try:
+        from modarith_b200.ecn import ecnmul
+        from modarith_b200.primes import NIST256 as P256
+        ne = 1 << 18
+        e = torch.randint(0, 256, (ne, 32), dtype=torch.uint8, device=dev, generator=gen)
+        import numpy as np
+        gx = torch.from_numpy(np.tile(np.frombuffer(P256.wgx.to_bytes(32, "big"), dtype=np.uint8), (ne, 1))).to(dev)
+        gy = torch.from_numpy(np.tile(np.frombuffer(P256.wgy.to_bytes(32, "big"), dtype=np.uint8), (ne, 1))).to(dev)
+        t = _time(lambda: ecnmul("NIST256", e, gx, gy), 2)
+        # algorithmic work of the reference's own schedule (weierstrass.c:494-542): 4 dbl + 3 add for the table,
+        # 64 x (4 dbl + 1 add); dbl = 10M + 3S, add = 14M (multiplications by b counted as M), one inversion + 2M
+        M, S = 64, 36
+        work = (4 + 256) * (10 * M + 3 * S) + (3 + 64) * 14 * M + mlib.products("NIST256", "modinv") + 2 * M
+        out["nist256_ecnmul"] = {"workload": "P-256 scalar multiplication (set+mul+get), 2^18 points", "value": ne / t,
+                                 "unit": "scalar-mults/s", "products_per_point": work,
+                                 "imad_frac": (ne / t * work / pk) if pk else None}
+        del e, gx, gy
+    except Exception as ex:           # the side measurement must never sink the headline line
+        out["nist256_ecnmul"] = {"error": str(ex)[:200]}
     for name, nel in (("NIST256", 1 << 24), ("X25519", 1 << 22)):
         F = Field(name, dev)
         a8 = torch.randint(0, 256, (nel, F.Nbytes), dtype=torch.uint8, device=dev, generator=gen)

@@ -150,6 +150,14 @@ MAB_DECLARE_FIELD(NIST256)
 MAB_DECLARE_FIELD(SECP256K1)
 MAB_DECLARE_FIELD(NIST256ORDER)
 
+/* ---- short-Weierstrass scalar multiplication (weierstrass.c) ------------------- */
+/* For each of n independent points: ecnXXXset(0, x, y, &P); ecnXXXmul(e, &P); ecnXXXget(&P, xo, yo)
+ * (weierstrass.c:415-427, 494-542, 333-349; curve constants curve.py:157-166).  All five arrays hold
+ * big-endian 32-byte strings, element i at offset 32*i, device pointers.  A point that is not on the
+ * curve, a zero scalar or a multiple of the group order give the point at infinity, reported as
+ * (0, 1) exactly as ecnXXXget does.  Constant time: fixed-window signed digits, masked table scans. */
+MAB_API int mab_NIST256_ecnmul(const char *e, const char *x, const char *y, char *xo, char *yo, size_t n, void *stream);
+
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */
 MAB_API int mab_X25519_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);

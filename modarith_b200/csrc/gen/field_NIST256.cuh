@@ -1963,6 +1963,9 @@ struct F_NIST256 {
   static MAB_DEV void set_one(uint32_t (&r)[8]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0xffffffffu; r[4] = 0xffffffffu; r[5] = 0xffffffffu; r[6] = 0xfffffffeu; r[7] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[8]) { r[0] = 0xfffffffeu; r[1] = 0xffffffffu; r[2] = 0xffffffffu; r[3] = 0x00000001u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000002u; r[7] = 0xfffffffeu; }
   static MAB_DEV void set_r2(uint32_t (&r)[8]) { r[0] = 0x00000003u; r[1] = 0x00000000u; r[2] = 0xffffffffu; r[3] = 0xfffffffbu; r[4] = 0xfffffffeu; r[5] = 0xffffffffu; r[6] = 0xfffffffdu; r[7] = 0x00000004u; }
+  // short-Weierstrass curve y^2 = x^3 - 3x + b (curve.py:157-166): b in stored form
+  static constexpr bool HAS_WEIERSTRASS = true;
+  static MAB_DEV void set_b(uint32_t (&r)[8]) { r[0] = 0x29c4bddfu; r[1] = 0xd89cdf62u; r[2] = 0x78843090u; r[3] = 0xacf005cdu; r[4] = 0xf7212ed6u; r[5] = 0xe5a220abu; r[6] = 0x04874834u; r[7] = 0xdc30061du; }
 
   // nres: multiply by R^2 mod p (monty.py:1386-1399); redc: multiply by 1 (monty.py:1402-1416)
   static MAB_DEV void nres(uint32_t (&r)[8], const uint32_t (&a)[8]) { uint32_t c[L]; set_r2(c); mul(r, a, c); }

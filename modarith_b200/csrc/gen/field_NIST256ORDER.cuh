@@ -5303,6 +5303,7 @@ struct F_NIST256ORDER {
   static MAB_DEV void set_one(uint32_t (&r)[8]) { r[0] = 0x039cdaafu; r[1] = 0x0c46353du; r[2] = 0x58e8617bu; r[3] = 0x43190552u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0xffffffffu; r[7] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[8]) { r[0] = 0x7e368fe1u; r[1] = 0x1015708fu; r[2] = 0x6ecc4511u; r[3] = 0x31c6c545u; r[4] = 0x98a19ea1u; r[5] = 0x5281fe89u; r[6] = 0x10c63fe8u; r[7] = 0x0279089eu; }
   static MAB_DEV void set_r2(uint32_t (&r)[8]) { r[0] = 0xbe79eea2u; r[1] = 0x83244c95u; r[2] = 0x49bd6fa6u; r[3] = 0x4699799cu; r[4] = 0x2b6bec59u; r[5] = 0x2845b239u; r[6] = 0xf3d95620u; r[7] = 0x66e12d94u; }
+  static constexpr bool HAS_WEIERSTRASS = false;
 
   // nres: multiply by R^2 mod p (monty.py:1386-1399); redc: multiply by 1 (monty.py:1402-1416)
   static MAB_DEV void nres(uint32_t (&r)[8], const uint32_t (&a)[8]) { uint32_t c[L]; set_r2(c); mul(r, a, c); }

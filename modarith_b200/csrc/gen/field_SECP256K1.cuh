@@ -5295,6 +5295,7 @@ struct F_SECP256K1 {
   static MAB_DEV void set_one(uint32_t (&r)[8]) { r[0] = 0x000003d1u; r[1] = 0x00000001u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[8]) { r[0] = 0xfffff85eu; r[1] = 0xfffffffdu; r[2] = 0xffffffffu; r[3] = 0xffffffffu; r[4] = 0xffffffffu; r[5] = 0xffffffffu; r[6] = 0xffffffffu; r[7] = 0xffffffffu; }
   static MAB_DEV void set_r2(uint32_t (&r)[8]) { r[0] = 0x000e90a1u; r[1] = 0x000007a2u; r[2] = 0x00000001u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
+  static constexpr bool HAS_WEIERSTRASS = false;
 
   // nres: multiply by R^2 mod p (monty.py:1386-1399); redc: multiply by 1 (monty.py:1402-1416)
   static MAB_DEV void nres(uint32_t (&r)[8], const uint32_t (&a)[8]) { uint32_t c[L]; set_r2(c); mul(r, a, c); }

@@ -1411,6 +1411,7 @@ struct F_X25519 {
   static MAB_DEV void set_one(uint32_t (&r)[8]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[8]) { r[0] = 0x4a0ea0b0u; r[1] = 0xc4ee1b27u; r[2] = 0xad2fe478u; r[3] = 0x2f431806u; r[4] = 0x3dfbd7a7u; r[5] = 0x2b4d0099u; r[6] = 0x4fc1df0bu; r[7] = 0x2b832480u; }
   static MAB_DEV void set_r2(uint32_t (&r)[8]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
+  static constexpr bool HAS_WEIERSTRASS = false;
 
   // nres: copy (pseudo.py:952-962); redc: copy + final subtract (pseudo.py:965-976)
   static MAB_DEV void nres(uint32_t (&r)[8], const uint32_t (&a)[8]) { for (int i = 0; i < L; i++) r[i] = a[i]; }

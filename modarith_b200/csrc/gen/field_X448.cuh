@@ -2841,6 +2841,7 @@ struct F_X448 {
   static MAB_DEV void set_one(uint32_t (&r)[14]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; r[8] = 0x00000000u; r[9] = 0x00000000u; r[10] = 0x00000000u; r[11] = 0x00000000u; r[12] = 0x00000000u; r[13] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[14]) { r[0] = 0xfffffffeu; r[1] = 0xffffffffu; r[2] = 0xffffffffu; r[3] = 0xffffffffu; r[4] = 0xffffffffu; r[5] = 0xffffffffu; r[6] = 0xffffffffu; r[7] = 0xfffffffeu; r[8] = 0xffffffffu; r[9] = 0xffffffffu; r[10] = 0xffffffffu; r[11] = 0xffffffffu; r[12] = 0xffffffffu; r[13] = 0xffffffffu; }
   static MAB_DEV void set_r2(uint32_t (&r)[14]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; r[8] = 0x00000000u; r[9] = 0x00000000u; r[10] = 0x00000000u; r[11] = 0x00000000u; r[12] = 0x00000000u; r[13] = 0x00000000u; }
+  static constexpr bool HAS_WEIERSTRASS = false;
 
   // nres: copy (pseudo.py:952-962); redc: copy + final subtract (pseudo.py:965-976)
   static MAB_DEV void nres(uint32_t (&r)[14], const uint32_t (&a)[14]) { for (int i = 0; i < L; i++) r[i] = a[i]; }

@@ -1,0 +1,29 @@
+"""Batched short-Weierstrass scalar multiplication: the reference's
+`ecnXXXset` + `ecnXXXmul` + `ecnXXXget` (weierstrass.c:415-427,494-542,333-349) for n independent points.
+
+    xo, yo = ecnmul("NIST256", e, x, y)      # [n, 32] uint8 cuda tensors, big-endian like the reference's char*
+
+A point off the curve, a zero scalar or a multiple of the group order give (0, 1) (ecnXXXget of O).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as _lib
+
+
+def ecnmul(curve: str, e, x, y, xo=None, yo=None):
+    if curve != "NIST256":
+        raise ValueError("unsupported curve %r (have NIST256)" % curve)
+    lib = _lib.load()
+    for t in (e, x, y):
+        assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 2
+        assert t.shape == e.shape and t.shape[1] == 32 and t.is_contiguous()
+    n = e.shape[0]
+    xo = torch.empty_like(x) if xo is None else xo
+    yo = torch.empty_like(y) if yo is None else yo
+    stream = torch.cuda.current_stream(e.device).cuda_stream
+    with torch.cuda.device(e.device):
+        _lib.check(lib.mab_NIST256_ecnmul(e.data_ptr(), x.data_ptr(), y.data_ptr(), xo.data_ptr(), yo.data_ptr(), n, stream),
+                   "mab_NIST256_ecnmul")
+    return xo, yo

@@ -106,6 +106,12 @@ def emit_field_header(plan: Plan) -> str:
     out.append(_const_fn("set_one", words(plan.to_internal(1), L), L))
     out.append(_const_fn("set_roi", words(plan.to_internal(P.roi), L), L))
     out.append(_const_fn("set_r2", words(plan.R * plan.R % P.p, L), L))
+    if P.wb is not None:
+        out.append("  // short-Weierstrass curve y^2 = x^3 - 3x + b (curve.py:157-166): b in stored form\n")
+        out.append("  static constexpr bool HAS_WEIERSTRASS = true;\n")
+        out.append(_const_fn("set_b", words(plan.to_internal(P.wb), L), L))
+    else:
+        out.append("  static constexpr bool HAS_WEIERSTRASS = false;\n")
     out.append("\n")
     if plan.R != 1:
         out.append("  // nres: multiply by R^2 mod p (monty.py:1386-1399); redc: multiply by 1 (monty.py:1402-1416)\n")

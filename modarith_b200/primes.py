@@ -17,6 +17,11 @@ class Prime:
     a24: int | None = None
     cof: int | None = None
     generator: int | None = None
+    # short-Weierstrass curve y^2 = x^3 - 3x + b over this field (curve.py:157-166); None otherwise
+    wb: int | None = None
+    wgx: int | None = None
+    wgy: int | None = None
+    worder: int | None = None
 
     @property
     def nbits(self) -> int:
@@ -55,7 +60,11 @@ class Prime:
 
 X25519 = Prime("X25519", 2**255 - 19, "pseudo", a24=121665, cof=3, generator=9)
 X448 = Prime("X448", 2**448 - 2**224 - 1, "monty", a24=39081, cof=2, generator=5)
-NIST256 = Prime("NIST256", 2**256 - 2**224 + 2**192 + 2**96 - 1, "monty")
+NIST256 = Prime("NIST256", 2**256 - 2**224 + 2**192 + 2**96 - 1, "monty",
+                wb=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+                wgx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+                wgy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
+                worder=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551)
 
 # the three moduli of the hot path (BASELINE configs)
 PRIMES = {q.name: q for q in (X25519, X448, NIST256)}

@@ -125,6 +125,51 @@ def build_one(name, script, prime, generic, ladder, cflags):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def build_curve(cflags):
+    """oracle/_ref/libref_NIST256_curve.so: the reference's weierstrass.c as its own curve.py patches it
+    for NIST256 (curve.py:157-166,335-351 -- it runs monty.py for the field and the group order and pastes
+    field.c / curve.c / point.h into weierstrass.c and curve.h in the working directory)."""
+    work = tempfile.mkdtemp(prefix="mab_ref_curve_")
+    try:
+        bindir = os.path.join(work, "bin")
+        os.mkdir(bindir)
+        wrapper = os.path.join(bindir, "addchain")
+        with open(wrapper, "w") as f:
+            f.write("#!/bin/sh\nexec %s %s \"$@\"\n" % (sys.executable, os.path.join(HERE, "addchain_standin.py")))
+        os.chmod(wrapper, os.stat(wrapper).st_mode | stat.S_IEXEC)
+        py3 = os.path.join(bindir, "python3")
+        with open(py3, "w") as f:
+            f.write("#!/bin/sh\nexec %s \"$@\"\n" % sys.executable)
+        os.chmod(py3, os.stat(py3).st_mode | stat.S_IEXEC)
+        for fn in ("curve.py", "weierstrass.c", "curve.h", "testcurve.c"):
+            shutil.copy(os.path.join(REF, fn), os.path.join(work, fn))
+        with open(os.path.join(REF, "monty.py")) as f:
+            src = f.read()
+        with open(os.path.join(work, "monty.py"), "w") as f:
+            f.write(_patch_settings(src, False))
+        env = dict(os.environ, PATH=bindir + os.pathsep + os.environ["PATH"])
+        r = subprocess.run([sys.executable, "curve.py", "64", "NIST256"], cwd=work, env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if "Passed - OK" not in r.stdout:
+            raise RuntimeError("curve.py did not complete:\n" + r.stdout[-3000:])
+        with open(os.path.join(work, "weierstrass.c")) as f:
+            unit = f.read()
+        with open(os.path.join(work, "curve.h")) as f:
+            hdr = f.read()
+        unit = unit.replace('#include "curve.h"', hdr)
+        with open(os.path.join(HERE, "ref_curve_shim.c")) as f:
+            unit += "\n" + f.read()
+        os.makedirs(OUT, exist_ok=True)
+        csrc = os.path.join(OUT, "ref_NIST256_curve.c")
+        with open(csrc, "w") as f:
+            f.write(unit)
+        so = os.path.join(OUT, "libref_NIST256_curve.so")
+        subprocess.check_call(["gcc"] + cflags + ["-shared", "-fPIC", "-fopenmp", "-w", "-o", so, csrc])
+        return so
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def main():
     if not os.path.isdir(REF):
         print("reference tree %s not present: keeping any prebuilt oracle/_ref" % REF)
@@ -134,6 +179,7 @@ def main():
     for t in TARGETS:
         so = build_one(*t, cflags)
         print("built", so)
+    print("built", build_curve(cflags))
     return 0
 
 

@@ -274,3 +274,41 @@ def rfc7748(prime: Prime | str, bk: bytes, bu: bytes, twist_secure: bool = True)
         x2 = F.modmul(x2, D)
     x2 = F.modmul(x2, z2)                         # rfc7748.c:252
     return F.modexp(x2)[::-1]                     # rfc7748.c:254-255
+
+
+def ecnmul(prime: Prime | str, e: bytes, x: bytes, y: bytes):
+    """ecnXXXset(0,x,y,&P); ecnXXXmul(e,&P); ecnXXXget(&P,xo,yo) restated at value level
+    (weierstrass.c:415-427 set with validation, :494-542 multiply, :297-349 affine/get; curve
+    y^2 = x^3 - 3x + b, constants curve.py:157-166).  Big-endian Nbytes strings in and out.
+    The point at infinity (point off the curve, e = 0 mod order) is reported as (0, 1)."""
+    F = FieldOracle(prime)
+    P, p, nb = F.P, F.p, F.nbytes
+    xv, _ = F.modimp(x)
+    yv, _ = F.modimp(y)
+    on_curve = (yv * yv - (xv * xv * xv - 3 * xv + P.wb)) % p == 0      # setxy, weierstrass.c:364-396
+    k = int.from_bytes(e, "big")
+
+    def add(A, B):                      # affine group law with None = O
+        if A is None:
+            return B
+        if B is None:
+            return A
+        (x1, y1), (x2, y2) = A, B
+        if x1 == x2:
+            if (y1 + y2) % p == 0:
+                return None
+            lam = (3 * x1 * x1 - 3) * pow(2 * y1, -1, p) % p
+        else:
+            lam = (y2 - y1) * pow(x2 - x1, -1, p) % p
+        x3 = (lam * lam - x1 - x2) % p
+        return x3, (lam * (x1 - x3) - y1) % p
+
+    R, Q = None, ((xv, yv) if on_curve else None)
+    while k:
+        if k & 1:
+            R = add(R, Q)
+        Q = add(Q, Q)
+        k >>= 1
+    if R is None:
+        return (0).to_bytes(nb, "big"), (1).to_bytes(nb, "big")        # ecnXXXaffine of O
+    return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")

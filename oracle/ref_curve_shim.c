@@ -1,0 +1,21 @@
+/* oracle/ref_curve_shim.c -- TEST INFRASTRUCTURE ONLY.  Appended after the reference's weierstrass.c
+ * (patched by its own curve.py for NIST256) in a scratch translation unit: a batch driver around
+ * ecnXXXset / ecnXXXmul / ecnXXXget (weierstrass.c:415-427, 494-542, 333-349). */
+#include <stddef.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+__attribute__((visibility("default")))
+void ref_ecnmul_batch(const char *e, const char *x, const char *y, char *xo, char *yo, size_t n, int nthreads) {
+    long i;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (i = 0; i < (long)n; i++) {
+        point P;
+        ecn_nist256_set(0, x + (size_t)i * BYTES, y + (size_t)i * BYTES, &P);
+        ecn_nist256_mul(e + (size_t)i * BYTES, &P);
+        ecn_nist256_get(&P, xo + (size_t)i * BYTES, yo + (size_t)i * BYTES);
+    }
+}

@@ -137,7 +137,47 @@ def field_vectors(name):
     return out
 
 
+def ecn_vectors():
+    """weierstrass.c as patched by the reference's own curve.py for NIST256 (oracle/_ref/libref_NIST256_curve.so):
+    ecnXXXset + ecnXXXmul + ecnXXXget on generator multiples, with off-curve points, zero scalars, the group
+    order and order+-1, all-ones scalars and small scalars mixed in."""
+    P = ALL_PRIMES["NIST256"]
+    lib = ref("NIST256_curve")
+    rng = np.random.Generator(np.random.PCG64(1060))
+    G = (P.wgx.to_bytes(32, "big"), P.wgy.to_bytes(32, "big"))
+
+    def mul(e, x, y):
+        xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        lib.ref_ecnmul_batch(e, x, y, xo, yo, ctypes.c_size_t(1), 1)
+        return xo.raw[:32], yo.raw[:32]
+
+    rows = []
+    pts = [G]
+    for _ in range(10):
+        pts.append(mul(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), *G))
+    scalars = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, P.worder - 1, P.worder, P.worder + 1, (1 << 256) - 1, 1 << 255,
+               0x8888888888888888888888888888888888888888888888888888888888888888,
+               0x7777777777777777777777777777777777777777777777777777777777777777]
+    for k in scalars:
+        x, y = pts[len(rows) % len(pts)]
+        rows.append((k.to_bytes(32, "big"), x, y))
+    for i in range(24):
+        x, y = pts[i % len(pts)]
+        rows.append((rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), x, y))
+    bad = bytearray(pts[1][1]); bad[31] ^= 1
+    rows.append((rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), pts[1][0], bytes(bad)))       # off the curve
+    rows.append((rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), bytes(32), bytes(32)))          # (0,0)
+    rows.append((rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), b"\xff" * 32, pts[2][1]))      # x >= p
+    out = []
+    for e, x, y in rows:
+        xo, yo = mul(e, x, y)
+        out.append({"e": e.hex(), "x": x.hex(), "y": y.hex(), "xo": xo.hex(), "yo": yo.hex()})
+    return {"NIST256": out}
+
+
 def main():
+    with open(os.path.join(HERE, "ecn.json"), "w") as f:
+        json.dump(ecn_vectors(), f, indent=1)
     rfc = {
         "X25519": curve_vectors("X25519", "77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a",
                                 "5dab087e624a8a4b79e17f8b83800ee66f3bb1292618b6fd1c2f8b27ff88e0eb"),

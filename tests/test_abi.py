@@ -19,7 +19,7 @@ def built():
 
 def header_symbols():
     h = open(os.path.join(ROOT, "include", "modarith_b200.h")).read()
-    syms = set(re.findall(r"\b(mab_[a-z0-9_]+)\s*\(", h))
+    syms = set(re.findall(r"\b(mab_[A-Za-z0-9_]+)\s*\(", h))
     macro = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", h)
     for P in re.findall(r"MAB_DECLARE_FIELD\((\w+)\)\n", h):
         if P != "P":
@@ -31,7 +31,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(built):
     dll = ctypes.CDLL(built)
     want = header_symbols()
-    assert len(want) == 9 + 5 * 33 + 8
+    assert len(want) == 10 + 5 * 33 + 8
     for s in sorted(want):
         assert hasattr(dll, s), s
     assert want == set(mlib.exported_symbols())
