@@ -239,6 +239,15 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
         out["nist256_ecnmul"] = {"workload": "P-256 scalar multiplication (set+mul+get), 2^18 points", "value": ne / t,
                                  "unit": "scalar-mults/s", "products_per_point": work,
                                  "imad_frac": (ne / t * work / pk) if pk else None}
+        # Ed25519 (edwards.c): dbl = 3M + 4S, add = 11M + 1S (multiplication by d counted as M)
+        from modarith_b200.primes import X25519 as P255
+        gx = torch.from_numpy(np.tile(np.frombuffer(P255.ed_gx.to_bytes(32, "big"), dtype=np.uint8), (ne, 1))).to(dev)
+        gy = torch.from_numpy(np.tile(np.frombuffer(P255.ed_gy.to_bytes(32, "big"), dtype=np.uint8), (ne, 1))).to(dev)
+        t = _time(lambda: ecnmul("ED25519", e, gx, gy), 2)
+        work = (4 + 256) * (3 * M + 4 * S) + (3 + 64) * (11 * M + S) + mlib.products("X25519", "modinv") + 2 * M
+        out["ed25519_ecnmul"] = {"workload": "Ed25519 scalar multiplication (set+mul+get), 2^18 points", "value": ne / t,
+                                 "unit": "scalar-mults/s", "products_per_point": work,
+                                 "imad_frac": (ne / t * work / pk) if pk else None}
         del e, gx, gy
     except Exception as ex:           # the side measurement must never sink the headline line
         out["nist256_ecnmul"] = {"error": str(ex)[:200]}

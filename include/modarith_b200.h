@@ -157,6 +157,9 @@ MAB_DECLARE_FIELD(NIST256ORDER)
  * curve, a zero scalar or a multiple of the group order give the point at infinity, reported as
  * (0, 1) exactly as ecnXXXget does.  Constant time: fixed-window signed digits, masked table scans. */
 MAB_API int mab_NIST256_ecnmul(const char *e, const char *x, const char *y, char *xo, char *yo, size_t n, void *stream);
+/* The same three calls on the twisted Edwards curve Ed25519 (edwards.c:347-356, 435-484, 219-241; constants
+ * curve.py:85-94) over the 2^255-19 field code; the identity is reported as (0, 1). */
+MAB_API int mab_ED25519_ecnmul(const char *e, const char *x, const char *y, char *xo, char *yo, size_t n, void *stream);
 
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */

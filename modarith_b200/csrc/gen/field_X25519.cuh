@@ -1411,6 +1411,8 @@ struct F_X25519 {
   static MAB_DEV void set_one(uint32_t (&r)[8]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
   static MAB_DEV void set_roi(uint32_t (&r)[8]) { r[0] = 0x4a0ea0b0u; r[1] = 0xc4ee1b27u; r[2] = 0xad2fe478u; r[3] = 0x2f431806u; r[4] = 0x3dfbd7a7u; r[5] = 0x2b4d0099u; r[6] = 0x4fc1df0bu; r[7] = 0x2b832480u; }
   static MAB_DEV void set_r2(uint32_t (&r)[8]) { r[0] = 0x00000001u; r[1] = 0x00000000u; r[2] = 0x00000000u; r[3] = 0x00000000u; r[4] = 0x00000000u; r[5] = 0x00000000u; r[6] = 0x00000000u; r[7] = 0x00000000u; }
+  // twisted Edwards curve -x^2 + y^2 = 1 + d x^2 y^2 (curve.py:85-94): d in stored form
+  static MAB_DEV void set_ed_d(uint32_t (&r)[8]) { r[0] = 0x135978a3u; r[1] = 0x75eb4dcau; r[2] = 0x4141d8abu; r[3] = 0x00700a4du; r[4] = 0x7779e898u; r[5] = 0x8cc74079u; r[6] = 0x2b6ffe73u; r[7] = 0x52036ceeu; }
   static constexpr bool HAS_WEIERSTRASS = false;
 
   // nres: copy (pseudo.py:952-962); redc: copy + final subtract (pseudo.py:965-976)

@@ -3,4 +3,5 @@
 #define MAB_P X25519
 #define MAB_F F_X25519
 #define MAB_HAS_CURVE 1
+#define MAB_HAS_EDWARDS 1
 #include "mab_capi.inc"

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include "rfc7748_sm100.cuh"
 #include "weierstrass_sm100.cuh"
+#include "edwards_sm100.cuh"
 
 enum MabOp {
   OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_SQR, OP_MLI, OP_CPY, OP_NSQR, OP_PRO, OP_INV, OP_INVH,
@@ -327,8 +328,8 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
 // ecnXXXset + ecnXXXmul + ecnXXXget (weierstrass.c:415-427,494-542,333-349) for n independent points:
 // (xo, yo) = affine(e * (x, y)); all strings big-endian Nbytes as the reference's char* arguments;
 // a point that is not on the curve, a zero scalar or a multiple of the group order give (0, 1).
-template <class F> __global__ void __launch_bounds__(128) k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y,
-                                                                   uint8_t* xo, uint8_t* yo, size_t n, unsigned align) {
+template <class F, class G> __global__ void __launch_bounds__(128) k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y,
+                                                                            uint8_t* xo, uint8_t* yo, size_t n, unsigned align) {
   constexpr int L = F::L;
   static_assert(F::NBYTES == 4 * L, "whole-word byte strings");
   extern __shared__ uint32_t mab_smem[];
@@ -344,10 +345,10 @@ template <class F> __global__ void __launch_bounds__(128) k_ecnmul(const uint8_t
   aos_ld<L>(raw, y, i, align);
 #pragma unroll
   for (int j = 0; j < L; j++) yw[j] = mab_bswap(raw[L - 1 - j]);
-  typename Weierstrass<F>::Pt P;
-  Weierstrass<F>::set(P, xw, yw);
-  Weierstrass<F>::mul(P, ew, mab_smem + threadIdx.x, blockDim.x);
-  Weierstrass<F>::get(xw, yw, P);
+  typename G::Pt P;
+  G::set(P, xw, yw);
+  EcnMul<G>::mul(P, ew, mab_smem + threadIdx.x, blockDim.x);
+  G::get(xw, yw, P);
 #pragma unroll
   for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(xw[j]);
   aos_st<L>(xo, i, align, raw);

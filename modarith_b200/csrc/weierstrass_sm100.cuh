@@ -10,6 +10,7 @@
 // strings, which are unique, so only the values -- not the order of internal operations -- are pinned.
 #pragma once
 #include "mab_field.cuh"
+#include "ecnmul_sm100.cuh"
 
 template <class F> struct Weierstrass {
   static constexpr int L = F::L;
@@ -92,90 +93,5 @@ template <class F> struct Weierstrass {
     Fd::to_words(yw, y);
   }
 
-  // ---- ecnXXXmul (weierstrass.c:441-542) -------------------------------------------------------------
-  // tab: this thread's column of the table W[0..8] = O,P,..,8P in shared memory: coordinate c, word w of
-  // entry e at tab[((e*3+c)*L + w)*pitch]
-  static MAB_DEV void tab_st(uint32_t* tab, int pitch, int e, const Pt& P) {
-#pragma unroll
-    for (int w = 0; w < L; w++) {
-      tab[((e * 3 + 0) * L + w) * pitch] = P.x[w];
-      tab[((e * 3 + 1) * L + w) * pitch] = P.y[w];
-      tab[((e * 3 + 2) * L + w) * pitch] = P.z[w];
-    }
-  }
-  // constant-time lookup of digit d in [-8,8]: scan all nine entries, then negate y if d < 0
-  static MAB_DEV void select(Pt& R, const uint32_t* tab, int pitch, int d) {
-    const int m = d >> 31;
-    const uint32_t dabs = (uint32_t)((d ^ m) - m);
-#pragma unroll
-    for (int w = 0; w < L; w++) { R.x[w] = 0; R.y[w] = 0; R.z[w] = 0; }
-    MAB_NOUNROLL
-    for (uint32_t e = 0; e < 9; e++) {
-      const uint32_t mask = 0u - (uint32_t)(e == dabs);
-#pragma unroll
-      for (int w = 0; w < L; w++) {
-        R.x[w] |= tab[((e * 3 + 0) * L + w) * pitch] & mask;
-        R.y[w] |= tab[((e * 3 + 1) * L + w) * pitch] & mask;
-        R.z[w] |= tab[((e * 3 + 2) * L + w) * pitch] & mask;
-      }
-    }
-    uint32_t ny[L];
-    F::neg(ny, R.y);
-    Fd::cmv((uint32_t)m & 1u, ny, R.y);
-  }
-
-  // P <- e*P; e = plain scalar as little-endian words (the reference takes Nbytes big-endian bytes)
-  static MAB_DEV void mul(Pt& P, const uint32_t (&e)[L], uint32_t* tab, int pitch) {
-    Pt Q;
-    inf(Q);          tab_st(tab, pitch, 0, Q);
-    tab_st(tab, pitch, 1, P);
-    cpy(Q, P); dbl(Q);            tab_st(tab, pitch, 2, Q);     // 2P
-    Pt T;
-    cpy(T, Q); add(T, P);         tab_st(tab, pitch, 3, T);     // 3P
-    dbl(Q);                       tab_st(tab, pitch, 4, Q);     // 4P
-    { Pt U; cpy(U, Q); add(U, P); tab_st(tab, pitch, 5, U); }   // 5P
-    dbl(T);                       tab_st(tab, pitch, 6, T);     // 6P
-    add(T, P);                    tab_st(tab, pitch, 7, T);     // 7P
-    dbl(Q);                       tab_st(tab, pitch, 8, Q);     // 8P
-
-    // signed digits: nibble j plus the carry of nibble j-1, minus 16 when it exceeds 7 (weierstrass.c:513-526);
-    // processed from the top, so the carries are produced by a first pass from the bottom
-    constexpr int ND = 8 * L;                   // nibbles
-    uint32_t carries[L];                        // bit j of word j/32... one carry bit per nibble
-#pragma unroll
-    for (int w = 0; w < L; w++) carries[w] = 0;
-    uint32_t c = 0;
-#pragma unroll
-    for (int w = 0; w < L; w++) {
-      uint32_t cw = 0;
-#pragma unroll
-      for (int n = 0; n < 8; n++) {
-        const uint32_t v = ((e[w] >> (4 * n)) & 0xfu) + c;      // 0..16
-        c = (v > 7u) ? 1u : 0u;
-        cw |= c << n;
-      }
-      carries[w] = cw;                           // carry OUT of each nibble of this word
-    }
-    // top digit = final carry
-    select(P, tab, pitch, (int)c);
-    MAB_NOUNROLL
-    for (int j = ND - 1; j >= 0; j--) {
-      const int w = j >> 3, n = j & 7;
-      // digit j = nibble + carry_in - 16*carry_out
-      uint32_t ew = 0, cwd = 0, cprev = 0;
-#pragma unroll
-      for (int q = 0; q < L; q++) {              // static indexing only: pick word w with masks
-        const uint32_t mk = 0u - (uint32_t)(q == w);
-        ew |= e[q] & mk;
-        cwd |= carries[q] & mk;
-        if (q > 0) cprev |= carries[q - 1] & (0u - (uint32_t)(q == w));
-      }
-      const uint32_t cin = (n == 0) ? ((w == 0) ? 0u : (cprev >> 7) & 1u) : ((cwd >> (n - 1)) & 1u);
-      const uint32_t cout = (cwd >> n) & 1u;
-      const int d = (int)(((ew >> (4 * n)) & 0xfu) + cin) - (int)(cout << 4);
-      select(Q, tab, pitch, d);
-      dbl(P); dbl(P); dbl(P); dbl(P);
-      add(P, Q);
-    }
-  }
+  static MAB_DEV void neg(Pt& P) { uint32_t t[L]; F::neg(t, P.y); Fd::cpy(P.y, t); }    // weierstrass.c:62-65
 };

@@ -2,6 +2,7 @@
 `ecnXXXset` + `ecnXXXmul` + `ecnXXXget` (weierstrass.c:415-427,494-542,333-349) for n independent points.
 
     xo, yo = ecnmul("NIST256", e, x, y)      # [n, 32] uint8 cuda tensors, big-endian like the reference's char*
+    xo, yo = ecnmul("ED25519", e, x, y)      # twisted Edwards (edwards.c), identity reported as (0, 1)
 
 A point off the curve, a zero scalar or a multiple of the group order give (0, 1) (ecnXXXget of O).
 """
@@ -13,8 +14,8 @@ from . import lib as _lib
 
 
 def ecnmul(curve: str, e, x, y, xo=None, yo=None):
-    if curve != "NIST256":
-        raise ValueError("unsupported curve %r (have NIST256)" % curve)
+    if curve not in ("NIST256", "ED25519"):
+        raise ValueError("unsupported curve %r (have NIST256, ED25519)" % curve)
     lib = _lib.load()
     for t in (e, x, y):
         assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 2
@@ -24,6 +25,7 @@ def ecnmul(curve: str, e, x, y, xo=None, yo=None):
     yo = torch.empty_like(y) if yo is None else yo
     stream = torch.cuda.current_stream(e.device).cuda_stream
     with torch.cuda.device(e.device):
-        _lib.check(lib.mab_NIST256_ecnmul(e.data_ptr(), x.data_ptr(), y.data_ptr(), xo.data_ptr(), yo.data_ptr(), n, stream),
-                   "mab_NIST256_ecnmul")
+        fn = getattr(lib, "mab_%s_ecnmul" % curve)
+        _lib.check(fn(e.data_ptr(), x.data_ptr(), y.data_ptr(), xo.data_ptr(), yo.data_ptr(), n, stream),
+                   "mab_%s_ecnmul" % curve)
     return xo, yo

@@ -106,6 +106,9 @@ def emit_field_header(plan: Plan) -> str:
     out.append(_const_fn("set_one", words(plan.to_internal(1), L), L))
     out.append(_const_fn("set_roi", words(plan.to_internal(P.roi), L), L))
     out.append(_const_fn("set_r2", words(plan.R * plan.R % P.p, L), L))
+    if P.ed_d is not None:
+        out.append("  // twisted Edwards curve -x^2 + y^2 = 1 + d x^2 y^2 (curve.py:85-94): d in stored form\n")
+        out.append(_const_fn("set_ed_d", words(plan.to_internal(P.ed_d), L), L))
     if P.wb is not None:
         out.append("  // short-Weierstrass curve y^2 = x^3 - 3x + b (curve.py:157-166): b in stored form\n")
         out.append("  static constexpr bool HAS_WEIERSTRASS = true;\n")

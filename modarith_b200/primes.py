@@ -18,6 +18,11 @@ class Prime:
     cof: int | None = None
     generator: int | None = None
     # short-Weierstrass curve y^2 = x^3 - 3x + b over this field (curve.py:157-166); None otherwise
+    # twisted Edwards curve -x^2 + y^2 = 1 + d x^2 y^2 over this field (curve.py:85-94, ED25519); None otherwise
+    ed_d: int | None = None
+    ed_gx: int | None = None
+    ed_gy: int | None = None
+    ed_order: int | None = None
     wb: int | None = None
     wgx: int | None = None
     wgy: int | None = None
@@ -58,7 +63,11 @@ class Prime:
         return pow(q, (p - 1) >> k, p)
 
 
-X25519 = Prime("X25519", 2**255 - 19, "pseudo", a24=121665, cof=3, generator=9)
+X25519 = Prime("X25519", 2**255 - 19, "pseudo", a24=121665, cof=3, generator=9,
+               ed_d=0x52036CEE2B6FFE738CC740797779E89800700A4D4141D8AB75EB4DCA135978A3,
+               ed_gx=0x216936D3CD6E53FEC0A4E231FDD6DC5C692CC7609525A7B2C9562D608F25D51A,
+               ed_gy=0x6666666666666666666666666666666666666666666666666666666666666658,
+               ed_order=0x1000000000000000000000000000000014DEF9DEA2F79CD65812631A5CF5D3ED)
 X448 = Prime("X448", 2**448 - 2**224 - 1, "monty", a24=39081, cof=2, generator=5)
 NIST256 = Prime("NIST256", 2**256 - 2**224 + 2**192 + 2**96 - 1, "monty",
                 wb=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,

@@ -125,10 +125,10 @@ def build_one(name, script, prime, generic, ladder, cflags):
         shutil.rmtree(work, ignore_errors=True)
 
 
-def build_curve(cflags):
-    """oracle/_ref/libref_NIST256_curve.so: the reference's weierstrass.c as its own curve.py patches it
-    for NIST256 (curve.py:157-166,335-351 -- it runs monty.py for the field and the group order and pastes
-    field.c / curve.c / point.h into weierstrass.c and curve.h in the working directory)."""
+def build_curve(cflags, curve="NIST256", template="weierstrass.c"):
+    """oracle/_ref/libref_<curve>_curve.so: the reference's weierstrass.c / edwards.c as its own curve.py
+    patches it (curve.py:85-94,157-166,335-351 -- it runs pseudo.py/monty.py for the field and the group order
+    and pastes field.c / curve.c / point.h into the template and curve.h in the working directory)."""
     work = tempfile.mkdtemp(prefix="mab_ref_curve_")
     try:
         bindir = os.path.join(work, "bin")
@@ -141,29 +141,30 @@ def build_curve(cflags):
         with open(py3, "w") as f:
             f.write("#!/bin/sh\nexec %s \"$@\"\n" % sys.executable)
         os.chmod(py3, os.stat(py3).st_mode | stat.S_IEXEC)
-        for fn in ("curve.py", "weierstrass.c", "curve.h", "testcurve.c"):
+        for fn in ("curve.py", template, "curve.h", "testcurve.c"):
             shutil.copy(os.path.join(REF, fn), os.path.join(work, fn))
-        with open(os.path.join(REF, "monty.py")) as f:
-            src = f.read()
-        with open(os.path.join(work, "monty.py"), "w") as f:
-            f.write(_patch_settings(src, False))
+        for gen in ("monty.py", "pseudo.py"):
+            with open(os.path.join(REF, gen)) as f:
+                src = f.read()
+            with open(os.path.join(work, gen), "w") as f:
+                f.write(_patch_settings(src, False))
         env = dict(os.environ, PATH=bindir + os.pathsep + os.environ["PATH"])
-        r = subprocess.run([sys.executable, "curve.py", "64", "NIST256"], cwd=work, env=env,
+        r = subprocess.run([sys.executable, "curve.py", "64", curve], cwd=work, env=env,
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if "Passed - OK" not in r.stdout:
             raise RuntimeError("curve.py did not complete:\n" + r.stdout[-3000:])
-        with open(os.path.join(work, "weierstrass.c")) as f:
+        with open(os.path.join(work, template)) as f:
             unit = f.read()
         with open(os.path.join(work, "curve.h")) as f:
             hdr = f.read()
         unit = unit.replace('#include "curve.h"', hdr)
         with open(os.path.join(HERE, "ref_curve_shim.c")) as f:
-            unit += "\n" + f.read()
+            unit += "\n" + f.read().replace("ecn_nist256_", "ecn_%s_" % curve.lower())
         os.makedirs(OUT, exist_ok=True)
-        csrc = os.path.join(OUT, "ref_NIST256_curve.c")
+        csrc = os.path.join(OUT, "ref_%s_curve.c" % curve)
         with open(csrc, "w") as f:
             f.write(unit)
-        so = os.path.join(OUT, "libref_NIST256_curve.so")
+        so = os.path.join(OUT, "libref_%s_curve.so" % curve)
         subprocess.check_call(["gcc"] + cflags + ["-shared", "-fPIC", "-fopenmp", "-w", "-o", so, csrc])
         return so
     finally:
@@ -179,7 +180,8 @@ def main():
     for t in TARGETS:
         so = build_one(*t, cflags)
         print("built", so)
-    print("built", build_curve(cflags))
+    print("built", build_curve(cflags, "NIST256", "weierstrass.c"))
+    print("built", build_curve(cflags, "ED25519", "edwards.c"))
     return 0
 
 

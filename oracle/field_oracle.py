@@ -312,3 +312,31 @@ def ecnmul(prime: Prime | str, e: bytes, x: bytes, y: bytes):
     if R is None:
         return (0).to_bytes(nb, "big"), (1).to_bytes(nb, "big")        # ecnXXXaffine of O
     return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")
+
+
+def ecnmul_edwards(prime: Prime | str, e: bytes, x: bytes, y: bytes):
+    """ecnXXXset(0,x,y,&P); ecnXXXmul(e,&P); ecnXXXget(&P,xo,yo) of edwards.c restated at value level
+    (edwards.c:243-272 set with the on-curve check, :435-484 multiply, :184-241 affine/get) on the twisted
+    Edwards curve -x^2 + y^2 = 1 + d x^2 y^2 (curve.py:85-94).  The identity (and any point off the curve)
+    is reported as (0, 1)."""
+    F = FieldOracle(prime)
+    P, p, nb = F.P, F.p, F.nbytes
+    d = P.ed_d
+    xv, _ = F.modimp(x)
+    yv, _ = F.modimp(y)
+    if (yv * yv - xv * xv - 1 - d * xv * xv * yv * yv) % p != 0:
+        xv, yv = 0, 1
+    k = int.from_bytes(e, "big")
+
+    def add(A, B):
+        (x1, y1), (x2, y2) = A, B
+        t = d * x1 * x2 * y1 * y2 % p
+        return ((x1 * y2 + y1 * x2) * pow(1 + t, -1, p) % p, (y1 * y2 + x1 * x2) * pow(1 - t, -1, p) % p)
+
+    R, Q = (0, 1), (xv, yv)
+    while k:
+        if k & 1:
+            R = add(R, Q)
+        Q = add(Q, Q)
+        k >>= 1
+    return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")

@@ -58,5 +58,5 @@ def _ref(name):
 def ref_libs():
     """The reference's own generated C (oracle/_ref), when it has been built."""
     libs = {n: _ref(n) for n in ("X25519", "X448", "NIST256", "X25519_generic", "X448_generic",
-                                  "X25519_validate", "X448_validate", "SECP256K1", "NIST256ORDER", "NIST256_curve")}
+                                  "X25519_validate", "X448_validate", "SECP256K1", "NIST256ORDER", "NIST256_curve", "ED25519_curve")}
     return {k: v for k, v in libs.items() if v is not None}

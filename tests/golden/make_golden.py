@@ -137,14 +137,20 @@ def field_vectors(name):
     return out
 
 
-def ecn_vectors():
-    """weierstrass.c as patched by the reference's own curve.py for NIST256 (oracle/_ref/libref_NIST256_curve.so):
+def ecn_vectors(curve="NIST256"):
+    """weierstrass.c / edwards.c as patched by the reference's own curve.py (oracle/_ref/libref_<curve>_curve.so):
     ecnXXXset + ecnXXXmul + ecnXXXget on generator multiples, with off-curve points, zero scalars, the group
     order and order+-1, all-ones scalars and small scalars mixed in."""
-    P = ALL_PRIMES["NIST256"]
-    lib = ref("NIST256_curve")
+    if curve == "NIST256":
+        P = ALL_PRIMES["NIST256"]
+        G = (P.wgx.to_bytes(32, "big"), P.wgy.to_bytes(32, "big"))
+        order = P.worder
+    else:
+        P = ALL_PRIMES["X25519"]
+        G = (P.ed_gx.to_bytes(32, "big"), P.ed_gy.to_bytes(32, "big"))
+        order = P.ed_order
+    lib = ref(curve + "_curve")
     rng = np.random.Generator(np.random.PCG64(1060))
-    G = (P.wgx.to_bytes(32, "big"), P.wgy.to_bytes(32, "big"))
 
     def mul(e, x, y):
         xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
@@ -155,7 +161,7 @@ def ecn_vectors():
     pts = [G]
     for _ in range(10):
         pts.append(mul(rng.integers(0, 256, 32, dtype=np.uint8).tobytes(), *G))
-    scalars = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, P.worder - 1, P.worder, P.worder + 1, (1 << 256) - 1, 1 << 255,
+    scalars = [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, order - 1, order, order + 1, (8 * order) % (1 << 256), (1 << 256) - 1, 1 << 255,
                0x8888888888888888888888888888888888888888888888888888888888888888,
                0x7777777777777777777777777777777777777777777777777777777777777777]
     for k in scalars:
@@ -172,12 +178,12 @@ def ecn_vectors():
     for e, x, y in rows:
         xo, yo = mul(e, x, y)
         out.append({"e": e.hex(), "x": x.hex(), "y": y.hex(), "xo": xo.hex(), "yo": yo.hex()})
-    return {"NIST256": out}
+    return out
 
 
 def main():
     with open(os.path.join(HERE, "ecn.json"), "w") as f:
-        json.dump(ecn_vectors(), f, indent=1)
+        json.dump({"NIST256": ecn_vectors("NIST256"), "ED25519": ecn_vectors("ED25519")}, f, indent=1)
     rfc = {
         "X25519": curve_vectors("X25519", "77076d0a7318a57d3c16c17251b26645df4c2f87ebc0992ab177fba51db92c2a",
                                 "5dab087e624a8a4b79e17f8b83800ee66f3bb1292618b6fd1c2f8b27ff88e0eb"),

@@ -14,6 +14,7 @@
 #include "gen/field_NIST256ORDER.cuh"
 #include "rfc7748_sm100.cuh"
 #include "weierstrass_sm100.cuh"
+#include "edwards_sm100.cuh"
 
 enum SimOp {
   S_ADD, S_SUB, S_NEG, S_MUL, S_SQR, S_MLI, S_NSQR, S_PRO, S_INV, S_INVH, S_QR, S_QRH, S_SQRT, S_SQRTH,
@@ -101,7 +102,7 @@ template <class F> static void sim_rfc7748_shared_inversion(const unsigned char*
 }
 
 // ecnXXXset + ecnXXXmul + ecnXXXget on big-endian byte strings, table in a local array
-template <class F> static void sim_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y,
+template <class F, class G> static void sim_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y,
                                           unsigned char* xo, unsigned char* yo) {
   constexpr int L = F::L;
   uint32_t ew[L], xw[L], yw[L];
@@ -113,10 +114,10 @@ template <class F> static void sim_ecnmul(const unsigned char* e, const unsigned
     yw[pos >> 2] |= (uint32_t)y[b] << (8 * (pos & 3));
   }
   static uint32_t tab[9 * 3 * L];
-  typename Weierstrass<F>::Pt P;
-  Weierstrass<F>::set(P, xw, yw);
-  Weierstrass<F>::mul(P, ew, tab, 1);
-  Weierstrass<F>::get(xw, yw, P);
+  typename G::Pt P;
+  G::set(P, xw, yw);
+  EcnMul<G>::mul(P, ew, tab, 1);
+  G::get(xw, yw, P);
   for (int b = 0; b < 4 * L; b++) {
     int pos = 4 * L - 1 - b;
     xo[b] = (unsigned char)(xw[pos >> 2] >> (8 * (pos & 3)));
@@ -125,7 +126,8 @@ template <class F> static void sim_ecnmul(const unsigned char* e, const unsigned
 }
 
 extern "C" {
-void sim_NIST256_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y, unsigned char* xo, unsigned char* yo) { sim_ecnmul<F_NIST256>(e, x, y, xo, yo); }
+void sim_NIST256_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y, unsigned char* xo, unsigned char* yo) { sim_ecnmul<F_NIST256, Weierstrass<F_NIST256> >(e, x, y, xo, yo); }
+void sim_ED25519_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y, unsigned char* xo, unsigned char* yo) { sim_ecnmul<F_X25519, Edwards<F_X25519> >(e, x, y, xo, yo); }
 void sim_X25519_rfc7748_shared(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) { sim_rfc7748_shared_inversion<F_X25519>(bk, bu, bv, K); }
 void sim_X448_rfc7748_shared(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) { sim_rfc7748_shared_inversion<F_X448>(bk, bu, bv, K); }
 int sim_X25519_op(int op, const uint32_t* a, const uint32_t* b, uint32_t s, uint32_t* r, uint32_t* r2) { return sim_op<F_X25519>(op, a, b, s, r, r2); }

@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from field_oracle import ecnmul as oracle_ecnmul
+from field_oracle import ecnmul as oracle_ecnmul, ecnmul_edwards as oracle_ecnmul_edwards
 from modarith_b200.primes import ALL_PRIMES
 import util
 
@@ -25,26 +25,37 @@ def test_oracle_against_reference_vectors(golden_ecn):
         "7cf27b188d034f7e8a52380304b51ac3c08969e277f21b35a60b48fc47669978"
 
 
-def test_hostsim_against_reference_vectors(hostsim, golden_ecn):
-    for r in golden_ecn["NIST256"]:
+def test_edwards_oracle_against_reference_vectors(golden_ecn):
+    rows = golden_ecn["ED25519"]
+    assert sum(1 for r in rows if int(r["xo"], 16) == 0 and int(r["yo"], 16) == 1) >= 5
+    for r in rows:
+        xo, yo = oracle_ecnmul_edwards("X25519", bytes.fromhex(r["e"]), bytes.fromhex(r["x"]), bytes.fromhex(r["y"]))
+        assert (xo.hex(), yo.hex()) == (r["xo"], r["yo"]), r
+
+
+@pytest.mark.parametrize("curve", ["NIST256", "ED25519"])
+def test_hostsim_against_reference_vectors(hostsim, golden_ecn, curve):
+    fn = getattr(hostsim, "sim_%s_ecnmul" % curve)
+    for r in golden_ecn[curve]:
         xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
-        hostsim.sim_NIST256_ecnmul(bytes.fromhex(r["e"]), bytes.fromhex(r["x"]), bytes.fromhex(r["y"]), xo, yo)
+        fn(bytes.fromhex(r["e"]), bytes.fromhex(r["x"]), bytes.fromhex(r["y"]), xo, yo)
         assert (xo.raw[:32].hex(), yo.raw[:32].hex()) == (r["xo"], r["yo"]), r
 
 
-def _gpu(e, x, y):
+def _gpu(e, x, y, curve="NIST256"):
     import torch
     from modarith_b200.ecn import ecnmul
-    xo, yo = ecnmul("NIST256", torch.from_numpy(e).cuda(), torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    xo, yo = ecnmul(curve, torch.from_numpy(e).cuda(), torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
     torch.cuda.synchronize()
     return xo.cpu().numpy(), yo.cpu().numpy()
 
 
 @pytest.mark.gpu
-def test_gpu_against_reference_vectors(golden_ecn):
-    rows = golden_ecn["NIST256"]
+@pytest.mark.parametrize("curve", ["NIST256", "ED25519"])
+def test_gpu_against_reference_vectors(golden_ecn, curve):
+    rows = golden_ecn[curve]
     f = lambda k: np.frombuffer(b"".join(bytes.fromhex(r[k]) for r in rows), dtype=np.uint8).reshape(-1, 32).copy()
-    xo, yo = _gpu(f("e"), f("x"), f("y"))
+    xo, yo = _gpu(f("e"), f("x"), f("y"), curve)
     for i, r in enumerate(rows):
         assert (xo[i].tobytes().hex(), yo[i].tobytes().hex()) == (r["xo"], r["yo"]), (i, r)
 
@@ -65,6 +76,30 @@ def test_gpu_ecdh_property_and_reference_build(ref_libs):
         assert (ax[i].tobytes(), ay[i].tobytes()) == oracle_ecnmul("NIST256", a[i].tobytes(), gx[i].tobytes(), gy[i].tobytes())
     if "NIST256_curve" in ref_libs:
         lib = ref_libs["NIST256_curve"]
+        xo, yo = np.zeros_like(ax), np.zeros_like(ay)
+        lib.ref_ecnmul_batch(a.ctypes.data_as(ctypes.c_char_p), bx.ctypes.data_as(ctypes.c_char_p),
+                             by.ctypes.data_as(ctypes.c_char_p), xo.ctypes.data_as(ctypes.c_char_p),
+                             yo.ctypes.data_as(ctypes.c_char_p), ctypes.c_size_t(n), ctypes.c_int(0))
+        assert np.array_equal(xo, s1[0]) and np.array_equal(yo, s1[1])
+
+
+@pytest.mark.gpu
+def test_gpu_ed25519_property_and_reference_build(ref_libs):
+    """Ed25519: a*(b*G) == b*(a*G) on 4096 random pairs; every element against the reference's edwards.c build."""
+    Q = ALL_PRIMES["X25519"]
+    n = 4096
+    a, b = util.random_bytes(701, n, 32), util.random_bytes(702, n, 32)
+    gx = np.tile(np.frombuffer(Q.ed_gx.to_bytes(32, "big"), dtype=np.uint8), (n, 1))
+    gy = np.tile(np.frombuffer(Q.ed_gy.to_bytes(32, "big"), dtype=np.uint8), (n, 1))
+    ax, ay = _gpu(a, gx, gy, "ED25519")
+    bx, by = _gpu(b, gx, gy, "ED25519")
+    s1 = _gpu(a, bx, by, "ED25519")
+    s2 = _gpu(b, ax, ay, "ED25519")
+    assert np.array_equal(s1[0], s2[0]) and np.array_equal(s1[1], s2[1])
+    for i in range(0, n, 512):
+        assert (ax[i].tobytes(), ay[i].tobytes()) == oracle_ecnmul_edwards("X25519", a[i].tobytes(), gx[i].tobytes(), gy[i].tobytes())
+    if "ED25519_curve" in ref_libs:
+        lib = ref_libs["ED25519_curve"]
         xo, yo = np.zeros_like(ax), np.zeros_like(ay)
         lib.ref_ecnmul_batch(a.ctypes.data_as(ctypes.c_char_p), bx.ctypes.data_as(ctypes.c_char_p),
                              by.ctypes.data_as(ctypes.c_char_p), xo.ctypes.data_as(ctypes.c_char_p),
