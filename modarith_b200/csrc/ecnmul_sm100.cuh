@@ -87,8 +87,8 @@ template <class G> struct EcnMul {
       const uint32_t cin = (n == 0) ? ((w == 0) ? 0u : (cprev >> 7) & 1u) : ((cwd >> (n - 1)) & 1u);
       const uint32_t cout = (cwd >> n) & 1u;
       const int d = (int)(((ew >> (4 * n)) & 0xfu) + cin) - (int)(cout << 4);
-      select(Q, tab, pitch, d);
       G::dbl(P); G::dbl(P); G::dbl(P); G::dbl(P);
+      select(Q, tab, pitch, d);       // after the doublings: Q's 3L registers are not live across them
       G::add(P, Q);
     }
   }

@@ -328,7 +328,10 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
 // ecnXXXset + ecnXXXmul + ecnXXXget (weierstrass.c:415-427,494-542,333-349) for n independent points:
 // (xo, yo) = affine(e * (x, y)); all strings big-endian Nbytes as the reference's char* arguments;
 // a point that is not on the curve, a zero scalar or a multiple of the group order give (0, 1).
-template <class F, class G> __global__ void __launch_bounds__(128) k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y,
+#ifndef MAB_ECN_MINBLOCKS
+#define MAB_ECN_MINBLOCKS 1
+#endif
+template <class F, class G> __global__ void __launch_bounds__(128, MAB_ECN_MINBLOCKS) k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y,
                                                                             uint8_t* xo, uint8_t* yo, size_t n, unsigned align) {
   constexpr int L = F::L;
   static_assert(F::NBYTES == 4 * L, "whole-word byte strings");
