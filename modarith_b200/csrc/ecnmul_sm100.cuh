@@ -1,39 +1,60 @@
 // ecnmul_sm100.cuh -- the reference's constant-time fixed-window scalar multiplication ecnXXXmul
 // (weierstrass.c:441-542 and, identically, edwards.c:382-484) over any group G that provides
-// Pt{x,y,z}, inf, cpy, neg, add (P <- P+Q) and dbl: table O,P,..,8P in shared memory, nibbles recoded
+// Pt{x,y,z}, inf, cpy, neg, add (P <- P+Q) and dbl: table O,P,..,8P in shared memory or in a global
+// workspace slice (the kernel decides per group), nibbles recoded
 // to signed digits in [-8,7], every lookup a masked scan of all nine entries, 4 doublings + 1 addition
 // per digit.  One point per thread; nothing depends on the scalar except through masks.
 #pragma once
 #include "mab_field.cuh"
 
-template <class G> struct EcnMul {
+// PITCH > 0 fixes the stride between consecutive words of one thread's table / scratch column at compile
+// time (every access becomes base + immediate); PITCH == 0 takes it from the `pitch` argument.
+template <class G, int PITCH = 0> struct EcnMul {
   static constexpr int L = G::L;
   typedef typename G::Pt Pt;
+  static MAB_DEV int stride(int pitch) { return PITCH ? PITCH : pitch; }
 
-  // tab: this thread's column of the table W[0..8]: coordinate c, word w of entry e at
-  // tab[((e*3+c)*L + w)*pitch]
-  static MAB_DEV void tab_st(uint32_t* tab, int pitch, int e, const Pt& P) {
+  // tab: this thread's column of the table W[0..8] in 16-byte chunks: words 4q..4q+3 of coordinate c
+  // of entry e form chunk ((e*3+c)*L/4 + q), stored at tab[chunk*pitch] -- one vector load / store per
+  // chunk, and a warp's 32 chunks are one contiguous 512-byte run (no bank conflicts, full lines).
+  static_assert(L % 4 == 0, "table chunks are four words");
+  static constexpr int CH = L / 4;                 // chunks per coordinate
+  static MAB_DEV void chunk_st(uint4* tab, int sp, int chunk, const uint32_t* v) {
+    tab[(size_t)chunk * sp] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  static MAB_DEV void tab_st(uint4* tab, int pitch, int e, const Pt& P) {
+    const int sp = stride(pitch);
 #pragma unroll
-    for (int w = 0; w < L; w++) {
-      tab[((e * 3 + 0) * L + w) * pitch] = P.x[w];
-      tab[((e * 3 + 1) * L + w) * pitch] = P.y[w];
-      tab[((e * 3 + 2) * L + w) * pitch] = P.z[w];
+    for (int q = 0; q < CH; q++) {
+      chunk_st(tab, sp, (e * 3 + 0) * CH + q, P.x + 4 * q);
+      chunk_st(tab, sp, (e * 3 + 1) * CH + q, P.y + 4 * q);
+      chunk_st(tab, sp, (e * 3 + 2) * CH + q, P.z + 4 * q);
     }
   }
-  // constant-time lookup of digit d in [-8,8]: scan all nine entries, then negate if d < 0
-  static MAB_DEV void select(Pt& R, const uint32_t* tab, int pitch, int d) {
+  // constant-time lookup of digit d in [-8,8]: every one of the nine entries is loaded and merged under
+  // a mask (one LOP3 per word; the mask is made opaque so that the compiler can neither turn the scan
+  // into a branch around the loads nor into a select plus an OR), then the result is negated if d < 0
+  static MAB_DEV void pick(uint32_t* r, const uint4 v, uint32_t mask) {
+    r[0] |= v.x & mask;  r[1] |= v.y & mask;  r[2] |= v.z & mask;  r[3] |= v.w & mask;
+  }
+  static MAB_DEV void select(Pt& R, const uint4* tab, int pitch, int d) {
+    const int sp = stride(pitch);
     const int m = d >> 31;
     const uint32_t dabs = (uint32_t)((d ^ m) - m);
 #pragma unroll
     for (int w = 0; w < L; w++) { R.x[w] = 0; R.y[w] = 0; R.z[w] = 0; }
     MAB_NOUNROLL
     for (uint32_t e = 0; e < 9; e++) {
-      const uint32_t mask = 0u - (uint32_t)(e == dabs);
+      uint32_t hit = 0u - (uint32_t)(e == dabs);
+#ifndef MAB_HOSTSIM
+      asm volatile("" : "+r"(hit));
+#endif
+      const uint4* te = tab + (size_t)e * (3 * CH) * sp;
 #pragma unroll
-      for (int w = 0; w < L; w++) {
-        R.x[w] |= tab[((e * 3 + 0) * L + w) * pitch] & mask;
-        R.y[w] |= tab[((e * 3 + 1) * L + w) * pitch] & mask;
-        R.z[w] |= tab[((e * 3 + 2) * L + w) * pitch] & mask;
+      for (int q = 0; q < CH; q++) {
+        pick(R.x + 4 * q, te[(size_t)(0 * CH + q) * sp], hit);
+        pick(R.y + 4 * q, te[(size_t)(1 * CH + q) * sp], hit);
+        pick(R.z + 4 * q, te[(size_t)(2 * CH + q) * sp], hit);
       }
     }
     Pt N;
@@ -42,18 +63,24 @@ template <class G> struct EcnMul {
     G::cmv((uint32_t)m & 1u, N, R);
   }
 
-  // P <- e*P; e = plain scalar as little-endian words (the reference takes Nbytes big-endian bytes)
-  static MAB_DEV void mul(Pt& P, const uint32_t (&e)[L], uint32_t* tab, int pitch) {
-    Pt Q, T;
-    G::inf(Q);                        tab_st(tab, pitch, 0, Q);
-    tab_st(tab, pitch, 1, P);
-    G::cpy(Q, P); G::dbl(Q);          tab_st(tab, pitch, 2, Q);     // 2P
-    G::cpy(T, Q); G::add(T, P);       tab_st(tab, pitch, 3, T);     // 3P
-    G::dbl(Q);                        tab_st(tab, pitch, 4, Q);     // 4P
-    { Pt U; G::cpy(U, Q); G::add(U, P); tab_st(tab, pitch, 5, U); } // 5P
-    G::dbl(T);                        tab_st(tab, pitch, 6, T);     // 6P
-    G::add(T, P);                     tab_st(tab, pitch, 7, T);     // 7P
-    G::dbl(Q);                        tab_st(tab, pitch, 8, Q);     // 8P
+  // P <- e*P; e = plain scalar as little-endian words (the reference takes Nbytes big-endian bytes).
+  // scr, when given, is a 2L-word column (same stride as the table) that holds the scalar and the
+  // recoding carries during the loop instead of 2L registers; it may be indexed dynamically.
+  // z: a zero the compiler cannot see, handed to the group law (Weierstrass::Seq); 0 when not needed.
+  static MAB_DEV void mul(Pt& P, const uint32_t (&e)[L], uint4* tab, int pitch, uint32_t* scr = nullptr, uint32_t z = 0) {
+    const int sp = stride(pitch);
+    {
+      Pt Q, T;
+      G::inf(Q);                        tab_st(tab, pitch, 0, Q);
+      tab_st(tab, pitch, 1, P);
+      G::cpy(Q, P); G::dbl(Q);          tab_st(tab, pitch, 2, Q);     // 2P
+      G::cpy(T, Q); G::add(T, P);       tab_st(tab, pitch, 3, T);     // 3P
+      G::dbl(Q);                        tab_st(tab, pitch, 4, Q);     // 4P
+      { Pt U; G::cpy(U, Q); G::add(U, P); tab_st(tab, pitch, 5, U); } // 5P
+      G::dbl(T);                        tab_st(tab, pitch, 6, T);     // 6P
+      G::add(T, P);                     tab_st(tab, pitch, 7, T);     // 7P
+      G::dbl(Q);                        tab_st(tab, pitch, 8, Q);     // 8P
+    }
 
     // signed digits (weierstrass.c:513-526): digit j = nibble j + carry_in - 16*carry_out with
     // carry_out = (nibble + carry_in > 7).  The loop runs from the top digit down, so the carries are
@@ -72,24 +99,36 @@ template <class G> struct EcnMul {
       }
       carries[w] = cw;
     }
+    if (scr) {
+#pragma unroll
+      for (int w = 0; w < L; w++) { scr[w * sp] = e[w]; scr[(L + w) * sp] = carries[w]; }
+    }
     select(P, tab, pitch, (int)c);                // top digit = final carry
+    typename G::Seq q = G::seq(z);
     MAB_NOUNROLL
     for (int j = ND - 1; j >= 0; j--) {
       const int w = j >> 3, n = j & 7;
       uint32_t ew = 0, cwd = 0, cprev = 0;
+      if (scr) {
+        ew = scr[w * sp];
+        cwd = scr[(L + w) * sp];
+        cprev = scr[(L + (w > 0 ? w - 1 : 0)) * sp];
+      } else {
 #pragma unroll
-      for (int q = 0; q < L; q++) {               // pick word w with masks: no dynamically indexed register
-        const uint32_t mk = 0u - (uint32_t)(q == w);
-        ew |= e[q] & mk;
-        cwd |= carries[q] & mk;
-        if (q > 0) cprev |= carries[q - 1] & mk;
+        for (int q = 0; q < L; q++) {             // pick word w with masks: no dynamically indexed register
+          const uint32_t mk = 0u - (uint32_t)(q == w);
+          ew |= e[q] & mk;
+          cwd |= carries[q] & mk;
+          if (q > 0) cprev |= carries[q - 1] & mk;
+        }
       }
       const uint32_t cin = (n == 0) ? ((w == 0) ? 0u : (cprev >> 7) & 1u) : ((cwd >> (n - 1)) & 1u);
       const uint32_t cout = (cwd >> n) & 1u;
       const int d = (int)(((ew >> (4 * n)) & 0xfu) + cin) - (int)(cout << 4);
-      G::dbl(P); G::dbl(P); G::dbl(P); G::dbl(P);
+      G::dbl(P, q); G::dbl(P, q); G::dbl(P, q); G::dbl(P, q);
+      Pt Q;
       select(Q, tab, pitch, d);       // after the doublings: Q's 3L registers are not live across them
-      G::add(P, Q);
+      G::add(P, Q, q);
     }
   }
 };

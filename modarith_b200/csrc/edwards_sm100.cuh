@@ -11,6 +11,9 @@ template <class F> struct Edwards {
   static constexpr int L = F::L;
   typedef Field<F> Fd;
   struct Pt { uint32_t x[L], y[L], z[L]; };
+  // k_ecnmul: where the fixed-window table lives and how many CTAs per SM the registers are cut for (measured)
+  static constexpr bool ECN_GLOBAL_TABLE = false;
+  static constexpr int ECN_MINBLOCKS = 2;
 
   static MAB_DEV void inf(Pt& P) { Fd::zer(P.x); Fd::one(P.y); Fd::one(P.z); }           // edwards.c:170-175
   static MAB_DEV void cpy(Pt& R, const Pt& P) { Fd::cpy(R.x, P.x); Fd::cpy(R.y, P.y); Fd::cpy(R.z, P.z); }
@@ -18,6 +21,10 @@ template <class F> struct Edwards {
   static MAB_DEV void neg(Pt& P) { uint32_t t[L]; F::neg(t, P.x); Fd::cpy(P.x, t); }     // edwards.c:66-69
 
   // P <- P + Q  (a = -1): 10M + 1S + 1 mul-by-d
+  struct Seq {};                                   // no ordering needed on this field (see Weierstrass::Seq)
+  static MAB_DEV Seq seq(uint32_t) { return Seq(); }
+  static MAB_DEV void add(Pt& P, const Pt& Q, Seq&) { add(P, Q); }
+  static MAB_DEV void dbl(Pt& P, Seq&) { dbl(P); }
   static MAB_DEV void add(Pt& P, const Pt& Q) {
     uint32_t A[L], B[L], C[L], D[L], E[L], Ff[L], Gg[L], dd[L];
     F::set_ed_d(dd);

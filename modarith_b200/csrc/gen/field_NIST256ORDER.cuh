@@ -167,8 +167,8 @@ struct F_NIST256ORDER {
         "madc.hi.cc.u32 t28, %12, %23, t28;\n\t"
         "madc.lo.cc.u32 t29, %14, %23, t29;\n\t"
         "madc.hi.cc.u32 t30, %14, %23, t30;\n\t"
-        "addc.u32 t31, 0x0, 0x0;\n\t"
-        "add.cc.u32 t32, t1, t17;\n\t"
+        "addc.cc.u32 t31, 0x0, 0x0;\n\t"
+        "addc.cc.u32 t32, t1, t17;\n\t"
         "addc.cc.u32 t33, t2, t18;\n\t"
         "addc.cc.u32 t34, t3, t19;\n\t"
         "addc.cc.u32 t35, t4, t20;\n\t"
@@ -630,8 +630,8 @@ struct F_NIST256ORDER {
     w_ = (((uint64_t)a_4_i * b_7_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)(uint32_t)(a_6_i * b_7_i) + t29 + cf_; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (((uint64_t)a_6_i * b_7_i) >> 32) + t30 + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t31 = (uint32_t)w_;
-    w_ = (uint64_t)t1 + t17; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t31 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t1 + t17 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t2 + t18 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t19 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t4 + t20 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
@@ -1005,8 +1005,8 @@ struct F_NIST256ORDER {
         "madc.hi.cc.u32 t28, %13, %14, t28;\n\t"
         "addc.u32 t29, 0x0, 0x0;\n\t"
         "mad.lo.cc.u32 t29, %14, %15, t29;\n\t"
-        "madc.hi.u32 t30, %14, %15, 0x0;\n\t"
-        "add.cc.u32 t32, t2, t18;\n\t"
+        "madc.hi.cc.u32 t30, %14, %15, 0x0;\n\t"
+        "addc.cc.u32 t32, t2, t18;\n\t"
         "addc.cc.u32 t33, t3, t19;\n\t"
         "addc.cc.u32 t34, t4, t20;\n\t"
         "addc.cc.u32 t35, t5, t21;\n\t"
@@ -1416,8 +1416,8 @@ struct F_NIST256ORDER {
     w_ = (((uint64_t)a_5_i * a_6_i) >> 32) + t28 + cf_; t28 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)0x0u + 0x0u + cf_; t29 = (uint32_t)w_;
     w_ = (uint64_t)(uint32_t)(a_6_i * a_7_i) + t29; t29 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (((uint64_t)a_6_i * a_7_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_;
-    w_ = (uint64_t)t2 + t18; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (((uint64_t)a_6_i * a_7_i) >> 32) + 0x0u + cf_; t30 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t2 + t18 + cf_; t32 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t3 + t19 + cf_; t33 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t4 + t20 + cf_; t34 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t5 + t21 + cf_; t35 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);

@@ -13,6 +13,8 @@
 #ifdef MAB_HOSTSIM
 #define MAB_DEV inline
 #define MAB_NOUNROLL
+struct uint4 { uint32_t x, y, z, w; };           // the 16-byte vector type of the device build
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = {x, y, z, w}; return v; }
 static inline uint32_t mab_sim_prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint8_t by[8];
   for (int i = 0; i < 4; i++) { by[i] = (uint8_t)(a >> (8 * i)); by[4 + i] = (uint8_t)(b >> (8 * i)); }

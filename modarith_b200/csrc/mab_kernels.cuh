@@ -328,34 +328,66 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
 // ecnXXXset + ecnXXXmul + ecnXXXget (weierstrass.c:415-427,494-542,333-349) for n independent points:
 // (xo, yo) = affine(e * (x, y)); all strings big-endian Nbytes as the reference's char* arguments;
 // a point that is not on the curve, a zero scalar or a multiple of the group order give (0, 1).
-#ifndef MAB_ECN_MINBLOCKS
-#define MAB_ECN_MINBLOCKS 1
+// Where the fixed-window table lives is a property of the group (G::ECN_GLOBAL_TABLE, G::ECN_MINBLOCKS;
+// -DMAB_ECN_GLOBAL_TABLE / -DMAB_ECN_MINBLOCKS override both groups for experiments).  The table is
+// 9 entries x 3 coordinates x L words = 864 B per point for L = 8:
+//   shared memory   two 128-thread CTAs per SM at most; measured best for Ed25519, whose digit step is
+//                   short enough that the lookups matter (36.1 vs 31.0 M/s);
+//   global memory   each resident CTA owns one slice of a workspace that only resident CTAs touch
+//                   (148 x 3 x 108 KB = 48 MB: L2 resident, re-used block after block); shared memory
+//                   then only keeps the scalar and its recoding carries, and a third CTA fits --
+//                   measured best for P-256, whose long reduction chains need the extra warps (11.3 vs
+//                   9.6 M/s).
+#ifdef MAB_ECN_GLOBAL_TABLE
+#define MAB_ECN_GLOBAL(G) (MAB_ECN_GLOBAL_TABLE != 0)
+#else
+#define MAB_ECN_GLOBAL(G) (G::ECN_GLOBAL_TABLE)
 #endif
-template <class F, class G> __global__ void __launch_bounds__(128, MAB_ECN_MINBLOCKS) k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y,
-                                                                            uint8_t* xo, uint8_t* yo, size_t n, unsigned align) {
+#ifdef MAB_ECN_MINBLOCKS
+#define MAB_ECN_MB(G) (MAB_ECN_MINBLOCKS)
+#else
+#define MAB_ECN_MB(G) (G::ECN_MINBLOCKS)
+#endif
+#define MAB_ECN_THREADS 128
+// Persistent grid: CTA b handles the 128-point blocks b, b + gridDim.x, ...
+template <class F, class G> __global__ void __launch_bounds__(MAB_ECN_THREADS, MAB_ECN_MB(G))
+k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y, uint8_t* xo, uint8_t* yo, size_t n, unsigned align,
+         uint4* tabws) {
   constexpr int L = F::L;
   static_assert(F::NBYTES == 4 * L, "whole-word byte strings");
-  extern __shared__ uint32_t mab_smem[];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t raw[L], ew[L], xw[L], yw[L];
-  aos_ld<L>(raw, e, i, align);
+  extern __shared__ uint4 mab_smem4[];
+  typedef EcnMul<G, MAB_ECN_THREADS> M;
+  uint4* tab;
+  uint32_t* scr;
+  if (MAB_ECN_GLOBAL(G)) {
+    tab = tabws + (size_t)blockIdx.x * (9 * 3 * (L / 4) * MAB_ECN_THREADS) + threadIdx.x;
+    scr = reinterpret_cast<uint32_t*>(mab_smem4) + threadIdx.x;
+  } else {
+    tab = mab_smem4 + threadIdx.x;
+    scr = nullptr;
+  }
+  for (size_t blk = blockIdx.x; blk * MAB_ECN_THREADS < n; blk += gridDim.x) {
+    const size_t i = blk * MAB_ECN_THREADS + threadIdx.x;
+    if (i >= n) break;
+    uint32_t raw[L], ew[L], xw[L], yw[L];
+    aos_ld<L>(raw, e, i, align);
 #pragma unroll
-  for (int j = 0; j < L; j++) ew[j] = mab_bswap(raw[L - 1 - j]);
-  aos_ld<L>(raw, x, i, align);
+    for (int j = 0; j < L; j++) ew[j] = mab_bswap(raw[L - 1 - j]);
+    aos_ld<L>(raw, x, i, align);
 #pragma unroll
-  for (int j = 0; j < L; j++) xw[j] = mab_bswap(raw[L - 1 - j]);
-  aos_ld<L>(raw, y, i, align);
+    for (int j = 0; j < L; j++) xw[j] = mab_bswap(raw[L - 1 - j]);
+    aos_ld<L>(raw, y, i, align);
 #pragma unroll
-  for (int j = 0; j < L; j++) yw[j] = mab_bswap(raw[L - 1 - j]);
-  typename G::Pt P;
-  G::set(P, xw, yw);
-  EcnMul<G>::mul(P, ew, mab_smem + threadIdx.x, blockDim.x);
-  G::get(xw, yw, P);
+    for (int j = 0; j < L; j++) yw[j] = mab_bswap(raw[L - 1 - j]);
+    typename G::Pt P;
+    G::set(P, xw, yw);
+    M::mul(P, ew, tab, MAB_ECN_THREADS, scr, align >> 16);   // align <= 16: a zero ptxas cannot fold
+    G::get(xw, yw, P);
 #pragma unroll
-  for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(xw[j]);
-  aos_st<L>(xo, i, align, raw);
+    for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(xw[j]);
+    aos_st<L>(xo, i, align, raw);
 #pragma unroll
-  for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(yw[j]);
-  aos_st<L>(yo, i, align, raw);
+    for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(yw[j]);
+    aos_st<L>(yo, i, align, raw);
+  }
 }

@@ -16,48 +16,87 @@ template <class F> struct Weierstrass {
   static constexpr int L = F::L;
   typedef Field<F> Fd;
   struct Pt { uint32_t x[L], y[L], z[L]; };
+  // k_ecnmul: where the fixed-window table lives and how many CTAs per SM the registers are cut for (measured)
+  static constexpr bool ECN_GLOBAL_TABLE = true;
+  static constexpr int ECN_MINBLOCKS = 3;
 
   static MAB_DEV void inf(Pt& P) { Fd::zer(P.x); Fd::one(P.y); Fd::zer(P.z); }          // weierstrass.c:283-288
   static MAB_DEV void cpy(Pt& R, const Pt& P) { Fd::cpy(R.x, P.x); Fd::cpy(R.y, P.y); Fd::cpy(R.z, P.z); }
   static MAB_DEV void cmv(uint32_t d, const Pt& Q, Pt& P) { Fd::cmv(d, Q.x, P.x); Fd::cmv(d, Q.y, P.y); Fd::cmv(d, Q.z, P.z); }
 
+  // Ordering of the multiplications inside add/dbl.  The formulas offer ptxas up to three independent
+  // multiplications at a time; it interleaves them all, and with the carry chains of the Montgomery
+  // reduction that needs more predicate registers than exist (measured: ~1200 of 15000 instructions per
+  // digit were predicate saves and restores).  Seq makes every multiplication's first operand word
+  // depend on the result of the one DEPTH multiplications earlier through `x ^ (r & z)` with a zero z
+  // that the compiler cannot see (one LOP3 per multiplication), which bounds the overlap to DEPTH.
+#ifndef MAB_ECN_CHAIN
+#define MAB_ECN_CHAIN 2
+#endif
+  struct Seq {
+    uint32_t z, l0, l1;
+    MAB_DEV void done(uint32_t w) {
+      if (MAB_ECN_CHAIN == 1) l0 = w;
+      else { l0 = l1; l1 = w; }
+    }
+  };
+  static MAB_DEV void mulq(Seq& q, uint32_t (&r)[L], const uint32_t (&a)[L], const uint32_t (&b)[L]) {
+    if (MAB_ECN_CHAIN == 0) { F::mul(r, a, b); return; }
+    uint32_t a2[L];
+    Fd::cpy(a2, a);
+    a2[0] ^= q.l0 & q.z;
+    F::mul(r, a2, b);
+    q.done(r[L - 1]);
+  }
+  static MAB_DEV void sqrq(Seq& q, uint32_t (&r)[L], const uint32_t (&a)[L]) {
+    if (MAB_ECN_CHAIN == 0) { F::sqr(r, a); return; }
+    uint32_t a2[L];
+    Fd::cpy(a2, a);
+    a2[0] ^= q.l0 & q.z;
+    F::sqr(r, a2);
+    q.done(r[L - 1]);
+  }
+
   // P <- P + Q, complete (eprint 2015/1060 Algorithm 4, a = -3): 12M + 2 mul-by-b + 29 add/sub
-  static MAB_DEV void add(Pt& P, const Pt& Q) {
+  static MAB_DEV Seq seq(uint32_t z) { Seq q = {z, 0, 0}; return q; }
+  static MAB_DEV void add(Pt& P, const Pt& Q) { Seq q = seq(0); add(P, Q, q); }
+  static MAB_DEV void dbl(Pt& P) { Seq q = seq(0); dbl(P, q); }
+  static MAB_DEV void add(Pt& P, const Pt& Q, Seq& q) {
     uint32_t b[L], t0[L], t1[L], t2[L], t3[L], t4[L], x3[L], y3[L], z3[L];
     F::set_b(b);
-    F::mul(t0, P.x, Q.x);  F::mul(t1, P.y, Q.y);  F::mul(t2, P.z, Q.z);
-    F::add(t3, P.x, P.y);  F::add(t4, Q.x, Q.y);  F::mul(t3, t3, t4);
+    mulq(q, t0, P.x, Q.x);  mulq(q, t1, P.y, Q.y);  mulq(q, t2, P.z, Q.z);
+    F::add(t3, P.x, P.y);  F::add(t4, Q.x, Q.y);  mulq(q, t3, t3, t4);
     F::add(t4, t0, t1);    F::sub(t3, t3, t4);    F::add(t4, P.y, P.z);
-    F::add(x3, Q.y, Q.z);  F::mul(t4, t4, x3);    F::add(x3, t1, t2);
+    F::add(x3, Q.y, Q.z);  mulq(q, t4, t4, x3);    F::add(x3, t1, t2);
     F::sub(t4, t4, x3);    F::add(x3, P.x, P.z);  F::add(y3, Q.x, Q.z);
-    F::mul(x3, x3, y3);    F::add(y3, t0, t2);    F::sub(y3, x3, y3);
-    F::mul(z3, b, t2);     F::sub(x3, y3, z3);    F::add(z3, x3, x3);
+    mulq(q, x3, x3, y3);    F::add(y3, t0, t2);    F::sub(y3, x3, y3);
+    mulq(q, z3, b, t2);     F::sub(x3, y3, z3);    F::add(z3, x3, x3);
     F::add(x3, x3, z3);    F::sub(z3, t1, x3);    F::add(x3, t1, x3);
-    F::mul(y3, b, y3);     F::add(t1, t2, t2);    F::add(t2, t1, t2);
+    mulq(q, y3, b, y3);     F::add(t1, t2, t2);    F::add(t2, t1, t2);
     F::sub(y3, y3, t2);    F::sub(y3, y3, t0);    F::add(t1, y3, y3);
     F::add(y3, t1, y3);    F::add(t1, t0, t0);    F::add(t0, t1, t0);
-    F::sub(t0, t0, t2);    F::mul(t1, t4, y3);    F::mul(t2, t0, y3);
-    F::mul(y3, x3, z3);    F::add(y3, y3, t2);    F::mul(x3, t3, x3);
-    F::sub(x3, x3, t1);    F::mul(z3, t4, z3);    F::mul(t1, t3, t0);
+    F::sub(t0, t0, t2);    mulq(q, t1, t4, y3);    mulq(q, t2, t0, y3);
+    mulq(q, y3, x3, z3);    F::add(y3, y3, t2);    mulq(q, x3, t3, x3);
+    F::sub(x3, x3, t1);    mulq(q, z3, t4, z3);    mulq(q, t1, t3, t0);
     F::add(z3, z3, t1);
     Fd::cpy(P.x, x3); Fd::cpy(P.y, y3); Fd::cpy(P.z, z3);
   }
 
   // P <- 2P, complete (Algorithm 6, a = -3): 8M + 3S + 2 mul-by-b + 21 add/sub
-  static MAB_DEV void dbl(Pt& P) {
+  static MAB_DEV void dbl(Pt& P, Seq& q) {
     uint32_t b[L], t0[L], t1[L], t2[L], t3[L], x3[L], y3[L], z3[L];
     F::set_b(b);
-    F::sqr(t0, P.x);       F::sqr(t1, P.y);       F::sqr(t2, P.z);
-    F::mul(t3, P.x, P.y);  F::add(t3, t3, t3);    F::mul(z3, P.x, P.z);
-    F::add(z3, z3, z3);    F::mul(y3, b, t2);     F::sub(y3, y3, z3);
+    sqrq(q, t0, P.x);       sqrq(q, t1, P.y);       sqrq(q, t2, P.z);
+    mulq(q, t3, P.x, P.y);  F::add(t3, t3, t3);    mulq(q, z3, P.x, P.z);
+    F::add(z3, z3, z3);    mulq(q, y3, b, t2);     F::sub(y3, y3, z3);
     F::add(x3, y3, y3);    F::add(y3, x3, y3);    F::sub(x3, t1, y3);
-    F::add(y3, t1, y3);    F::mul(y3, x3, y3);    F::mul(x3, x3, t3);
-    F::add(t3, t2, t2);    F::add(t2, t2, t3);    F::mul(z3, b, z3);
+    F::add(y3, t1, y3);    mulq(q, y3, x3, y3);    mulq(q, x3, x3, t3);
+    F::add(t3, t2, t2);    F::add(t2, t2, t3);    mulq(q, z3, b, z3);
     F::sub(z3, z3, t2);    F::sub(z3, z3, t0);    F::add(t3, z3, z3);
     F::add(z3, z3, t3);    F::add(t3, t0, t0);    F::add(t0, t3, t0);
-    F::sub(t0, t0, t2);    F::mul(t0, t0, z3);    F::add(y3, y3, t0);
-    F::mul(t0, P.y, P.z);  F::add(t0, t0, t0);    F::mul(z3, t0, z3);
-    F::sub(x3, x3, z3);    F::mul(z3, t0, t1);    F::add(z3, z3, z3);
+    F::sub(t0, t0, t2);    mulq(q, t0, t0, z3);    F::add(y3, y3, t0);
+    mulq(q, t0, P.y, P.z);  F::add(t0, t0, t0);    mulq(q, z3, t0, z3);
+    F::sub(x3, x3, z3);    mulq(q, z3, t0, t1);    F::add(z3, z3, z3);
     F::add(z3, z3, z3);
     Fd::cpy(P.x, x3); Fd::cpy(P.y, y3); Fd::cpy(P.z, z3);
   }

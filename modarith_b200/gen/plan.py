@@ -48,6 +48,9 @@ def _names(prefix, n):
 
 
 class Plan:
+    # reductions that consume the low half of the product first (Montgomery) order the merge after
+    # the last product chain, see Asm.link_cc; MAB_LINK=0 switches it off (experiment)
+    link_products = False
     family = "?"
 
     def __init__(self, prime: Prime):
@@ -97,14 +100,14 @@ class Plan:
     def build_mul(self):
         asm = Asm(self.name + ".mul")
         a, b = self._io(asm, ["a", "b"])
-        T = satmul.product(asm, a, b)
+        T = satmul.product(asm, a, b, link=self.link_products)
         self._outs(asm, self.reduce_wide(asm, T))
         return asm
 
     def build_sqr(self):
         asm = Asm(self.name + ".sqr")
         (a,) = self._io(asm, ["a"])
-        T = satmul.square(asm, a)
+        T = satmul.square(asm, a, link=self.link_products)
         self._outs(asm, self.reduce_wide(asm, T))
         return asm
 
@@ -512,6 +515,7 @@ class Montgomery(Plan):
     multiplies.  Stored values are fully reduced, in [0, p): 32L == Nbits leaves no
     spare bit for the reference's lazy "< 2p" results."""
     family = "monty"
+    link_products = os.environ.get("MAB_LINK", "1") != "0"
 
     def __init__(self, prime):
         super().__init__(prime)

@@ -35,6 +35,7 @@ class Asm:
         self.inputs = []       # external input names, in operand order
         self.outputs = []      # (external output name, internal reg)
         self.nocheck = set()   # instruction indices allowed to wrap (borrow-mask captures)
+        self.zero_cin = set()  # instruction indices whose carry-in is an ordering link: must be 0
 
     # ---- registers ------------------------------------------------------
     def tmp(self, n=None):
@@ -57,6 +58,22 @@ class Asm:
     def _emit(self, op, dst, srcs, cin=False, cout=False):
         self.ins.append((op, dst, tuple(srcs), cin, cout))
         return dst
+
+    def link_cc(self):
+        """Ordering link for the NEXT carry-consuming instruction: the most recent carry-capable
+        instruction (whose carry-out is provably zero and was not declared) is made to write CC, and
+        the next instruction, emitted with cin=True, reads that zero.  Costs no instruction; it only
+        gives ptxas a dependency, so that the consumer's chain cannot be started before the producer's
+        chain has finished (ptxas otherwise runs many carry chains as a wavefront and runs out of
+        predicate registers).  The interpreter checks that the carry really is zero."""
+        for k in range(len(self.ins) - 1, -1, -1):
+            op, d, srcs, cin, cout = self.ins[k]
+            if op in ("add", "sub", "madlo", "madhi"):
+                if not cout:
+                    self.ins[k] = (op, d, srcs, cin, True)
+                self.zero_cin.add(len(self.ins))
+                return True
+        return False
 
     def add(self, d, a, b, cin=False, cout=False):
         return self._emit("add", d, (a, b), cin, cout)
@@ -161,6 +178,10 @@ class Asm:
 
         for idx, (op, d, s, cin, cout) in enumerate(self.ins):
             c = cf if cin else 0
+            if idx in self.zero_cin:
+                assert cin, "ordering link without a consumer"
+                if c and strict:
+                    raise LostCarry("%s: ordering link at %d carries a non-zero carry" % (self.name, idx))
             if op == "add":
                 t = val(s[0]) + val(s[1]) + c
                 car = t >> 32

@@ -89,10 +89,13 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
         asm.wide_chain(slots, last_carry_to=None)
 
 
-def _merge(asm: Asm, E: _Acc, O: _Acc, nwords):
-    """T = E + O as one carry chain; returns list of nwords regs/literals."""
+def _merge(asm: Asm, E: _Acc, O: _Acc, nwords, link=False):
+    """T = E + O as one carry chain; returns list of nwords regs/literals.  link=True orders the
+    chain after the last product chain (Asm.link_cc) -- for reductions that consume the low words
+    first, where ptxas would otherwise pull every row's low windows forward."""
     T = []
     started = False
+    linked = False
     for k in range(nwords):
         e, o = E.src(k), O.src(k)
         if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
@@ -100,7 +103,9 @@ def _merge(asm: Asm, E: _Acc, O: _Acc, nwords):
             T.append(o if e == 0 else e)
             continue
         d = asm.tmp()
-        asm.add(d, e, o, cin=started, cout=(k < nwords - 1))
+        if link and not started:
+            linked = asm.link_cc()
+        asm.add(d, e, o, cin=(started or linked), cout=(k < nwords - 1))
         started = True
         T.append(d)
     return T
@@ -121,13 +126,13 @@ def product_eo(asm: Asm, a, b):
     return E, O
 
 
-def product(asm: Asm, a, b):
+def product(asm: Asm, a, b, link=False):
     """Return the 2L words (registers) of a*b; a, b are lists of L register names."""
     E, O = product_eo(asm, a, b)
-    return _merge(asm, E, O, 2 * len(a))
+    return _merge(asm, E, O, 2 * len(a), link=link)
 
 
-def square(asm: Asm, a):
+def square(asm: Asm, a, link=False):
     """Return the 2L words of a*a: 2 * sum_{i<j} a_i a_j 2^(32(i+j)) + sum a_i^2 2^(64 i).
 
     L(L-1)/2 off-diagonal wide products in even/odd chains, one funnel-shift
@@ -142,7 +147,7 @@ def square(asm: Asm, a):
         od = [(i + j, a[i], a[j]) for j in range(i + 1, L) if (i + j) % 2 == 1]
         _row_chain(asm, E, ev, n)
         _row_chain(asm, O, od, n)
-    S = _merge(asm, E, O, n)            # off-diagonal sum, < 2^(64L-1)
+    S = _merge(asm, E, O, n, link=link)            # off-diagonal sum, < 2^(64L-1)
     # double: D[k] = (S[k] << 1) | (S[k-1] >> 31)
     D = []
     for k in range(n):

@@ -113,10 +113,12 @@ template <class F, class G> static void sim_ecnmul(const unsigned char* e, const
     xw[pos >> 2] |= (uint32_t)x[b] << (8 * (pos & 3));
     yw[pos >> 2] |= (uint32_t)y[b] << (8 * (pos & 3));
   }
-  static uint32_t tab[9 * 3 * L];
+  static uint4 tab[9 * 3 * L / 4];
+  static uint32_t scr[2 * L];
   typename G::Pt P;
   G::set(P, xw, yw);
-  EcnMul<G>::mul(P, ew, tab, 1);
+  // odd scalars take the register path for the digits, even ones the scratch column the kernel uses
+  EcnMul<G>::mul(P, ew, tab, 1, (ew[0] & 1u) ? nullptr : scr);
   G::get(xw, yw, P);
   for (int b = 0; b < 4 * L; b++) {
     int pos = 4 * L - 1 - b;
