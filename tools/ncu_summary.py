@@ -2,6 +2,7 @@
 """Summarise an `ncu --page raw --csv` export into the handful of counters the design argues from.
 
     python tools/ncu_summary.py gpurun_out/prof_raw.csv > profiles/rN_<name>.txt
+    python tools/ncu_summary.py --launches gpurun_out/launches.csv > profiles/rN_launches.txt
 """
 import csv
 import io
@@ -51,6 +52,8 @@ def main(path):
         key = (short, r[ix.get("launch__grid_size", 0)] if "launch__grid_size" in ix else "")
         if key in seen:
             continue
+        if any("nan" in r[ix[k]] for k, _ in KEYS if k in ix):     # a replay that lost its counters: take the next launch
+            continue
         seen[key] = 1
         print("== %s" % short)
         for k, label in KEYS:
@@ -59,5 +62,31 @@ def main(path):
         print()
 
 
+def launches(path):
+    """Per-kernel totals and shares of a `--metrics gpu__time_duration.sum --csv` launch list."""
+    txt = open(path).read()
+    txt = txt[txt.index('"ID"'):]
+    rows = list(csv.reader(io.StringIO(txt)))
+    ix = {h: i for i, h in enumerate(rows[0])}
+    agg = {}
+    for r in rows[1:]:
+        if len(r) <= ix["Metric Value"] or r[ix["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "")
+        unit = r[ix["Metric Unit"]]
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
+        a = agg.setdefault((name, r[ix["Grid Size"]], r[ix["Block Size"]]), [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    tot = sum(a[1] for a in agg.values())
+    print("# kernel | grid | block | launches | mean us | total us | share")
+    for (name, g, b), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%s | %s | %s | %d | %.1f | %.1f | %.1f%%" % (name, g, b, n, t / n, t, 100 * t / tot))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--launches":
+        launches(sys.argv[2])
+    else:
+        main(sys.argv[1])

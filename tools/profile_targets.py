@@ -21,6 +21,21 @@ for curve, nb, n in (("X25519", 32, 1 << 20), ("X448", 56, 1 << 19)):
     for _ in range(2):
         rfc7748(curve, k, u)
 torch.cuda.synchronize()
+if "--no-ecn" not in sys.argv:
+    import numpy as np
+    from modarith_b200.ecn import ecnmul
+    from modarith_b200.primes import PRIMES, X25519
+    n = 1 << 18
+    e = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g)
+    for curve, gx, gy in (("NIST256", PRIMES["NIST256"].wgx, PRIMES["NIST256"].wgy), ("ED25519", X25519.ed_gx, X25519.ed_gy)):
+        x = torch.from_numpy(np.tile(np.frombuffer(gx.to_bytes(32, "big"), dtype=np.uint8), (n, 1))).to(dev)
+        y = torch.from_numpy(np.tile(np.frombuffer(gy.to_bytes(32, "big"), dtype=np.uint8), (n, 1))).to(dev)
+        for _ in range(2):
+            ecnmul(curve, e, x, y)
+    torch.cuda.synchronize()
+if "--ladders-only" in sys.argv:
+    print("done")
+    sys.exit(0)
 for name, n in (("NIST256", 1 << 22), ("X25519", 1 << 22)):
     F = Field(name)
     a = torch.randint(0, 256, (n, F.Nbytes), dtype=torch.uint8, device=dev, generator=g)
