@@ -160,6 +160,15 @@ MAB_API int mab_NIST256_ecnmul(const char *e, const char *x, const char *y, char
 /* The same three calls on the twisted Edwards curve Ed25519 (edwards.c:347-356, 435-484, 219-241; constants
  * curve.py:85-94) over the 2^255-19 field code; the identity is reported as (0, 1). */
 MAB_API int mab_ED25519_ecnmul(const char *e, const char *x, const char *y, char *xo, char *yo, size_t n, void *stream);
+/* Double multiplication, the verification building block (nist256.c:251):
+ * ecnXXXset(0, x1, y1, &P); ecnXXXset(0, x2, y2, &Q); ecnXXXmul2(e, &P, f, &Q, &R); ecnXXXget(&R, xo, yo)
+ * (weierstrass.c:545-572 / edwards.c:486-513): (xo, yo) = e*(x1,y1) + f*(x2,y2).  Same string conventions.
+ * The reference's routine is variable time (it skips zero digits); this one does the same work for every
+ * point.  e = f = 0 gives (0, 1) (the reference reads outside its digit array in that case). */
+MAB_API int mab_NIST256_ecnmul2(const char *e, const char *x1, const char *y1, const char *f, const char *x2, const char *y2,
+                                char *xo, char *yo, size_t n, void *stream);
+MAB_API int mab_ED25519_ecnmul2(const char *e, const char *x1, const char *y1, const char *f, const char *x2, const char *y2,
+                                char *xo, char *yo, size_t n, void *stream);
 
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */

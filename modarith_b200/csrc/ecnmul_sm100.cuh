@@ -37,14 +37,14 @@ template <class G, int PITCH = 0> struct EcnMul {
   static MAB_DEV void pick(uint32_t* r, const uint4 v, uint32_t mask) {
     r[0] |= v.x & mask;  r[1] |= v.y & mask;  r[2] |= v.z & mask;  r[3] |= v.w & mask;
   }
-  static MAB_DEV void select(Pt& R, const uint4* tab, int pitch, int d) {
+  template <int NE = 9> static MAB_DEV void select(Pt& R, const uint4* tab, int pitch, int d) {
     const int sp = stride(pitch);
     const int m = d >> 31;
     const uint32_t dabs = (uint32_t)((d ^ m) - m);
 #pragma unroll
     for (int w = 0; w < L; w++) { R.x[w] = 0; R.y[w] = 0; R.z[w] = 0; }
     MAB_NOUNROLL
-    for (uint32_t e = 0; e < 9; e++) {
+    for (uint32_t e = 0; e < NE; e++) {
       uint32_t hit = 0u - (uint32_t)(e == dabs);
 #ifndef MAB_HOSTSIM
       asm volatile("" : "+r"(hit));
@@ -129,6 +129,60 @@ template <class G, int PITCH = 0> struct EcnMul {
       Pt Q;
       select(Q, tab, pitch, d);       // after the doublings: Q's 3L registers are not live across them
       G::add(P, Q, q);
+    }
+  }
+
+  // R <- e*P + f*Q  (ecnXXXmul2, weierstrass.c:545-572 / edwards.c:486-513; ECDSA / EdDSA verification).
+  // Joint signed digits w_i = (bit_i(3e) - bit_i(e)) + 3 (bit_i(3f) - bit_i(f)) in [-4,4] (dnaf,
+  // weierstrass.c:463-492), table O, P, Q-P, Q, Q+P, digits i = 8*Nbytes+7 .. 1 from the top: one
+  // doubling, then +W[w_i] or -W[-w_i].  The reference skips leading and zero digits (it is variable
+  // time by design: the inputs of a verification are public); a warp would execute every branch anyway,
+  // so here every digit does the doubling and one addition of a masked-scan-selected entry (O for a zero
+  // digit) -- same result, constant work per point, no divergence.
+  // scr: 4(L+1)-word column: the +1 and -1 digit positions of e and of f as bit masks.
+  static constexpr int SCR2 = 4 * (L + 1);
+  static MAB_DEV void naf_masks(uint32_t* plus, uint32_t* minus, int sp, const uint32_t (&e)[L]) {
+    uint32_t c = 0, prev = 0;
+#pragma unroll
+    for (int w = 0; w <= L; w++) {
+      const uint32_t ew = (w < L) ? e[w] : 0u;
+      const uint32_t two = (ew << 1) | (prev >> 31);             // word w of 2e
+      prev = ew;
+      const uint64_t t = (uint64_t)ew + two + c;                 // word w of 3e
+      c = (uint32_t)(t >> 32);
+      const uint32_t t3 = (uint32_t)t;
+      plus[w * sp] = t3 & ~ew;
+      minus[w * sp] = ew & ~t3;
+    }
+  }
+  static MAB_DEV void mul2(Pt& R, const uint32_t (&e)[L], const Pt& P, const uint32_t (&f)[L], const Pt& Q, uint4* tab,
+                           int pitch, uint32_t* scr, uint32_t z = 0) {
+    const int sp = stride(pitch);
+    {
+      Pt T, N;
+      G::inf(T);                                     tab_st(tab, pitch, 0, T);     // O
+      tab_st(tab, pitch, 1, P);                                                    // P
+      tab_st(tab, pitch, 3, Q);                                                    // Q
+      G::cpy(N, P); G::neg(N); G::cpy(T, Q); G::add(T, N);  tab_st(tab, pitch, 2, T);     // Q-P
+      G::cpy(T, Q); G::add(T, P);                    tab_st(tab, pitch, 4, T);     // Q+P
+    }
+    uint32_t* pe = scr;
+    uint32_t* me = scr + (size_t)(L + 1) * sp;
+    uint32_t* pf = scr + (size_t)2 * (L + 1) * sp;
+    uint32_t* mf = scr + (size_t)3 * (L + 1) * sp;
+    naf_masks(pe, me, sp, e);
+    naf_masks(pf, mf, sp, f);
+    G::inf(R);
+    typename G::Seq q = G::seq(z);
+    MAB_NOUNROLL
+    for (int i = 32 * L + 7; i >= 1; i--) {
+      const int w = i >> 5, b = i & 31;
+      const int de = (int)((pe[w * sp] >> b) & 1u) - (int)((me[w * sp] >> b) & 1u);
+      const int df = (int)((pf[w * sp] >> b) & 1u) - (int)((mf[w * sp] >> b) & 1u);
+      G::dbl(R, q);
+      Pt T;
+      select<5>(T, tab, pitch, de + 3 * df);
+      G::add(R, T, q);
     }
   }
 };

@@ -391,3 +391,58 @@ k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y, uint8_t* xo, uint
     aos_st<L>(yo, i, align, raw);
   }
 }
+
+// ecnXXXset x2 + ecnXXXmul2 + ecnXXXget (weierstrass.c:545-572 / edwards.c:486-513) for n independent
+// pairs: (xo, yo) = affine(e*(x1,y1) + f*(x2,y2)); same conventions and the same persistent grid /
+// table placement as k_ecnmul (the table has five entries here, the scratch column 4(L+1) words).
+template <class F, class G> __global__ void __launch_bounds__(MAB_ECN_THREADS, MAB_ECN_MB(G))
+k_ecnmul2(const uint8_t* e, const uint8_t* x1, const uint8_t* y1, const uint8_t* f, const uint8_t* x2, const uint8_t* y2,
+          uint8_t* xo, uint8_t* yo, size_t n, unsigned align, uint4* tabws) {
+  constexpr int L = F::L;
+  extern __shared__ uint4 mab_smem4[];
+  typedef EcnMul<G, MAB_ECN_THREADS> M;
+  uint4* tab;
+  uint32_t* scr;
+  if (MAB_ECN_GLOBAL(G)) {
+    tab = tabws + (size_t)blockIdx.x * (9 * 3 * (L / 4) * MAB_ECN_THREADS) + threadIdx.x;
+    scr = reinterpret_cast<uint32_t*>(mab_smem4) + threadIdx.x;
+  } else {
+    tab = mab_smem4 + threadIdx.x;
+    scr = reinterpret_cast<uint32_t*>(mab_smem4 + 5 * 3 * (L / 4) * MAB_ECN_THREADS) + threadIdx.x;
+  }
+  for (size_t blk = blockIdx.x; blk * MAB_ECN_THREADS < n; blk += gridDim.x) {
+    const size_t i = blk * MAB_ECN_THREADS + threadIdx.x;
+    if (i >= n) break;
+    uint32_t raw[L], ew[L], fw[L], xw[L], yw[L];
+    typename G::Pt P, Q, R;
+    aos_ld<L>(raw, x1, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) xw[j] = mab_bswap(raw[L - 1 - j]);
+    aos_ld<L>(raw, y1, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) yw[j] = mab_bswap(raw[L - 1 - j]);
+    G::set(P, xw, yw);
+    aos_ld<L>(raw, x2, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) xw[j] = mab_bswap(raw[L - 1 - j]);
+    aos_ld<L>(raw, y2, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) yw[j] = mab_bswap(raw[L - 1 - j]);
+    G::set(Q, xw, yw);
+    aos_ld<L>(raw, e, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) ew[j] = mab_bswap(raw[L - 1 - j]);
+    aos_ld<L>(raw, f, i, align);
+#pragma unroll
+    for (int j = 0; j < L; j++) fw[j] = mab_bswap(raw[L - 1 - j]);
+    M::mul2(R, ew, P, fw, Q, tab, MAB_ECN_THREADS, scr, align >> 16);
+    G::get(xw, yw, R);
+#pragma unroll
+    for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(xw[j]);
+    aos_st<L>(xo, i, align, raw);
+#pragma unroll
+    for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(yw[j]);
+    aos_st<L>(yo, i, align, raw);
+  }
+}
+

@@ -94,6 +94,10 @@ def load() -> ctypes.CDLL:
     lib.mab_NIST256_ecnmul.restype = c_int
     lib.mab_ED25519_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
     lib.mab_ED25519_ecnmul.restype = c_int
+    for name in ("mab_NIST256_ecnmul2", "mab_ED25519_ecnmul2"):
+        fn = getattr(lib, name)
+        fn.argtypes = [_P] * 8 + [c_size_t, c_void_p]
+        fn.restype = c_int
     for P in CURVES:
         fn = getattr(lib, "mab_%s_rfc7748" % P)
         fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
@@ -115,7 +119,7 @@ def exported_symbols():
     """Every symbol include/modarith_b200.h declares (used by the CPU-side ABI test)."""
     syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak",
             "mab_pipe_probe", "mab_release_workspaces", "mab_probe_unsat29_modmul",
-            "mab_NIST256_ecnmul", "mab_ED25519_ecnmul"]
+            "mab_NIST256_ecnmul", "mab_ED25519_ecnmul", "mab_NIST256_ecnmul2", "mab_ED25519_ecnmul2"]
     for P in PRIMES:
         syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
     for P in CURVES:

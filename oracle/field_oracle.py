@@ -340,3 +340,37 @@ def ecnmul_edwards(prime: Prime | str, e: bytes, x: bytes, y: bytes):
         Q = add(Q, Q)
         k >>= 1
     return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")
+
+
+def ecnmul2(prime: Prime | str, e: bytes, x1: bytes, y1: bytes, f: bytes, x2: bytes, y2: bytes):
+    """ecnXXXset(0,x1,y1,&P); ecnXXXset(0,x2,y2,&Q); ecnXXXmul2(e,&P,f,&Q,&R); ecnXXXget(&R,xo,yo)
+    (weierstrass.c:545-572 / edwards.c:486-513: R = e*P + f*Q by a joint signed-digit scan) restated at
+    value level as two single multiplications and one addition.  `prime` NIST256 -> the Weierstrass
+    curve, X25519 -> Ed25519.  A point off the curve is replaced by the identity, as ecnXXXset does."""
+    F = FieldOracle(prime)
+    P, p, nb = F.P, F.p, F.nbytes
+    a = ecnmul_edwards if P.wb is None else ecnmul
+    ax, ay = a(prime, e, x1, y1)
+    bx, by = a(prime, f, x2, y2)
+    A = (int.from_bytes(ax, "big"), int.from_bytes(ay, "big"))
+    B = (int.from_bytes(bx, "big"), int.from_bytes(by, "big"))
+    if P.wb is None:                                  # Edwards: complete affine law, identity (0, 1)
+        d = P.ed_d
+        t = d * A[0] * B[0] * A[1] * B[1] % p
+        R = ((A[0] * B[1] + A[1] * B[0]) * pow(1 + t, -1, p) % p, (A[1] * B[1] + A[0] * B[0]) * pow(1 - t, -1, p) % p)
+        return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")
+    # Weierstrass: (0, 1) is how ecnXXXget reports O (it is not on the curve, so it cannot be a real point)
+    inf = lambda T: T == (0, 1)
+    if inf(A):
+        R = B
+    elif inf(B):
+        R = A
+    else:
+        (u1, v1), (u2, v2) = A, B
+        if u1 == u2 and (v1 + v2) % p == 0:
+            R = (0, 1)
+        else:
+            lam = ((3 * u1 * u1 - 3) * pow(2 * v1, -1, p) if u1 == u2 else (v2 - v1) * pow(u2 - u1, -1, p)) % p
+            u3 = (lam * lam - u1 - u2) % p
+            R = (u3, (lam * (u1 - u3) - v1) % p)
+    return R[0].to_bytes(nb, "big"), R[1].to_bytes(nb, "big")

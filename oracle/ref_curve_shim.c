@@ -19,3 +19,22 @@ void ref_ecnmul_batch(const char *e, const char *x, const char *y, char *xo, cha
         ecn_nist256_get(&P, xo + (size_t)i * BYTES, yo + (size_t)i * BYTES);
     }
 }
+
+/* ecnXXXset x2 / ecnXXXmul2 / ecnXXXget (weierstrass.c:545-572, edwards.c:486-513): R = e*P + f*Q */
+__attribute__((visibility("default")))
+void ref_ecnmul2_batch(const char *e, const char *x1, const char *y1, const char *f, const char *x2, const char *y2,
+                       char *xo, char *yo, size_t n, int nthreads) {
+    long i;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (i = 0; i < (long)n; i++) {
+        point P, Q, R;
+        size_t o = (size_t)i * BYTES;
+        ecn_nist256_set(0, x1 + o, y1 + o, &P);
+        ecn_nist256_set(0, x2 + o, y2 + o, &Q);
+        ecn_nist256_mul2(e + o, &P, f + o, &Q, &R);
+        ecn_nist256_get(&R, xo + o, yo + o);
+    }
+}

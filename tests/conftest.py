@@ -29,6 +29,12 @@ def golden_ecn():
 
 
 @pytest.fixture(scope="session")
+def golden_ecn2():
+    with open(os.path.join(ROOT, "tests", "golden", "ecn2.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def golden_field():
     with open(os.path.join(ROOT, "tests", "golden", "field.json")) as f:
         return json.load(f)

@@ -127,7 +127,38 @@ template <class F, class G> static void sim_ecnmul(const unsigned char* e, const
   }
 }
 
+// ecnXXXset x2 + ecnXXXmul2 + ecnXXXget
+template <class F, class G> static void sim_ecnmul2(const unsigned char* e, const unsigned char* x1, const unsigned char* y1,
+                                           const unsigned char* f, const unsigned char* x2, const unsigned char* y2,
+                                           unsigned char* xo, unsigned char* yo) {
+  constexpr int L = F::L;
+  uint32_t w[6][L];
+  const unsigned char* src[6] = {e, x1, y1, f, x2, y2};
+  for (int k = 0; k < 6; k++) {
+    for (int j = 0; j < L; j++) w[k][j] = 0;
+    for (int b = 0; b < 4 * L; b++) {
+      int pos = 4 * L - 1 - b;
+      w[k][pos >> 2] |= (uint32_t)src[k][b] << (8 * (pos & 3));
+    }
+  }
+  static uint4 tab[9 * 3 * L / 4];
+  static uint32_t scr[4 * (L + 1)];
+  typename G::Pt P, Q, R;
+  G::set(P, w[1], w[2]);
+  G::set(Q, w[4], w[5]);
+  EcnMul<G>::mul2(R, w[0], P, w[3], Q, tab, 1, scr);
+  uint32_t xw[L], yw[L];
+  G::get(xw, yw, R);
+  for (int b = 0; b < 4 * L; b++) {
+    int pos = 4 * L - 1 - b;
+    xo[b] = (unsigned char)(xw[pos >> 2] >> (8 * (pos & 3)));
+    yo[b] = (unsigned char)(yw[pos >> 2] >> (8 * (pos & 3)));
+  }
+}
+
 extern "C" {
+void sim_NIST256_ecnmul2(const unsigned char* e, const unsigned char* x1, const unsigned char* y1, const unsigned char* f, const unsigned char* x2, const unsigned char* y2, unsigned char* xo, unsigned char* yo) { sim_ecnmul2<F_NIST256, Weierstrass<F_NIST256> >(e, x1, y1, f, x2, y2, xo, yo); }
+void sim_ED25519_ecnmul2(const unsigned char* e, const unsigned char* x1, const unsigned char* y1, const unsigned char* f, const unsigned char* x2, const unsigned char* y2, unsigned char* xo, unsigned char* yo) { sim_ecnmul2<F_X25519, Edwards<F_X25519> >(e, x1, y1, f, x2, y2, xo, yo); }
 void sim_NIST256_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y, unsigned char* xo, unsigned char* yo) { sim_ecnmul<F_NIST256, Weierstrass<F_NIST256> >(e, x, y, xo, yo); }
 void sim_ED25519_ecnmul(const unsigned char* e, const unsigned char* x, const unsigned char* y, unsigned char* xo, unsigned char* yo) { sim_ecnmul<F_X25519, Edwards<F_X25519> >(e, x, y, xo, yo); }
 void sim_X25519_rfc7748_shared(const unsigned char* bk, const unsigned char* bu, unsigned char* bv, int K) { sim_rfc7748_shared_inversion<F_X25519>(bk, bu, bv, K); }

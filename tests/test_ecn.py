@@ -105,3 +105,32 @@ def test_gpu_ed25519_property_and_reference_build(ref_libs):
                              by.ctypes.data_as(ctypes.c_char_p), xo.ctypes.data_as(ctypes.c_char_p),
                              yo.ctypes.data_as(ctypes.c_char_p), ctypes.c_size_t(n), ctypes.c_int(0))
         assert np.array_equal(xo, s1[0]) and np.array_equal(yo, s1[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve", ["NIST256", "ED25519"])
+def test_gpu_large_ragged_batch_is_position_independent(curve):
+    """More 128-point blocks than the persistent grid has CTAs (each CTA walks several blocks and re-uses
+    its table slice), a ragged last block, and an empty batch: every row must equal the row of the small
+    batch it was copied from, which the other tests pin to the reference."""
+    Q = ALL_PRIMES["X25519"]
+    gxv, gyv = (P.wgx, P.wgy) if curve == "NIST256" else (Q.ed_gx, Q.ed_gy)
+    base = 1000
+    e0 = util.random_bytes(811, base, 32)
+    e0[0] = 0                                              # zero scalar -> (0, 1)
+    gx = np.tile(np.frombuffer(gxv.to_bytes(32, "big"), dtype=np.uint8), (base, 1))
+    gy = np.tile(np.frombuffer(gyv.to_bytes(32, "big"), dtype=np.uint8), (base, 1))
+    gy[1, 31] ^= 1                                         # a point that is not on the curve -> (0, 1)
+    x0, y0 = _gpu(e0, gx, gy, curve)
+    assert x0[0].tobytes() == bytes(32) and y0[0].tobytes() == (1).to_bytes(32, "big")
+    assert x0[1].tobytes() == bytes(32) and y0[1].tobytes() == (1).to_bytes(32, "big")
+    ora = oracle_ecnmul if curve == "NIST256" else oracle_ecnmul_edwards
+    name = "NIST256" if curve == "NIST256" else "X25519"
+    for i in (2, 499, 999):
+        assert (x0[i].tobytes(), y0[i].tobytes()) == ora(name, e0[i].tobytes(), gx[i].tobytes(), gy[i].tobytes())
+    n = 230 * base + 77                                    # 1798 blocks of 128 for a grid of a few hundred CTAs
+    idx = (np.arange(n) * 7919) % base
+    xo, yo = _gpu(e0[idx], gx[idx], gy[idx], curve)
+    assert np.array_equal(xo, x0[idx]) and np.array_equal(yo, y0[idx])
+    xe, ye = _gpu(e0[:0], gx[:0], gy[:0], curve)
+    assert xe.shape == (0, 32) and ye.shape == (0, 32)

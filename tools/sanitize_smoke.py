@@ -36,5 +36,17 @@ for name in ("X25519", "X448", "NIST256"):
     bits = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda", generator=g)
     F.modcsw(bits, x, y); F.modcmv(bits, x, y); F.nres(x, r); F.redc(x, r); F.modnsqr(r, 3); F.modcpy(x, r)
     F.modexp(r)
+# scalar multiplication: ragged batch, table slices in the pooled global workspace (P-256) / shared memory (Ed25519)
+import numpy as np  # noqa: E402
+from modarith_b200.ecn import ecnmul  # noqa: E402
+from modarith_b200.primes import PRIMES, X25519  # noqa: E402
+n = 300
+e = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+for curve, gx, gy in (("NIST256", PRIMES["NIST256"].wgx, PRIMES["NIST256"].wgy), ("ED25519", X25519.ed_gx, X25519.ed_gy)):
+    x = torch.from_numpy(np.tile(np.frombuffer(gx.to_bytes(32, "big"), dtype=np.uint8), (n, 1))).cuda()
+    y = torch.from_numpy(np.tile(np.frombuffer(gy.to_bytes(32, "big"), dtype=np.uint8), (n, 1))).cuda()
+    xo, yo = ecnmul(curve, e, x, y)
+    xo2, yo2 = ecnmul(curve, e, x, y)
+    assert torch.equal(xo, xo2) and torch.equal(yo, yo2)
 torch.cuda.synchronize()
 print("sanitize smoke done")
