@@ -239,6 +239,15 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
         out["nist256_ecnmul"] = {"workload": "P-256 scalar multiplication (set+mul+get), 2^18 points", "value": ne / t,
                                  "unit": "scalar-mults/s", "products_per_point": work,
                                  "imad_frac": (ne / t * work / pk) if pk else None}
+        # e*P + f*Q (ecnXXXmul2): this build does one doubling and one addition for each of the 263 joint digits
+        from modarith_b200.ecn import ecnmul2
+        n2 = ne // 2
+        f2 = torch.randint(0, 256, (n2, 32), dtype=torch.uint8, device=dev, generator=gen)
+        t = _time(lambda: ecnmul2("NIST256", e[:n2], gx[:n2], gy[:n2], f2, gx[:n2], gy[:n2]), 2)
+        work2 = 263 * (10 * M + 3 * S + 14 * M) + 2 * 14 * M + mlib.products("NIST256", "modinv") + 2 * M
+        out["nist256_ecnmul2"] = {"workload": "P-256 e*P + f*Q (set x2 + mul2 + get), 2^17 pairs", "value": n2 / t,
+                                  "unit": "double-mults/s", "products_per_pair": work2,
+                                  "imad_frac": (n2 / t * work2 / pk) if pk else None}
         # Ed25519 (edwards.c): dbl = 3M + 4S, add = 11M + 1S (multiplication by d counted as M)
         from modarith_b200.primes import X25519 as P255
         gx = torch.from_numpy(np.tile(np.frombuffer(P255.ed_gx.to_bytes(32, "big"), dtype=np.uint8), (ne, 1))).to(dev)
@@ -248,7 +257,12 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
         out["ed25519_ecnmul"] = {"workload": "Ed25519 scalar multiplication (set+mul+get), 2^18 points", "value": ne / t,
                                  "unit": "scalar-mults/s", "products_per_point": work,
                                  "imad_frac": (ne / t * work / pk) if pk else None}
-        del e, gx, gy
+        t = _time(lambda: ecnmul2("ED25519", e[:n2], gx[:n2], gy[:n2], f2, gx[:n2], gy[:n2]), 2)
+        work2 = 263 * (3 * M + 4 * S + 11 * M + S) + 2 * (11 * M + S) + mlib.products("X25519", "modinv") + 2 * M
+        out["ed25519_ecnmul2"] = {"workload": "Ed25519 e*P + f*Q (set x2 + mul2 + get), 2^17 pairs", "value": n2 / t,
+                                  "unit": "double-mults/s", "products_per_pair": work2,
+                                  "imad_frac": (n2 / t * work2 / pk) if pk else None}
+        del e, gx, gy, f2
     except Exception as ex:           # the side measurement must never sink the headline line
         out["nist256_ecnmul"] = {"error": str(ex)[:200]}
     for name, nel in (("NIST256", 1 << 24), ("X25519", 1 << 22)):
