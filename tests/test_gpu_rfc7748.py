@@ -197,6 +197,28 @@ def test_host_path_numpy_pageable():
     assert np.array_equal(out, _gpu("X448", k, u))
 
 
+@pytest.mark.parametrize("curve,nb", [("X25519", 32), ("X448", 56)])
+def test_host_path_pinned_zero_copy_and_staged_agree(curve, nb, monkeypatch):
+    """Pinned buffers: the kernel reads and writes host memory itself; MAB_HOST_ZEROCOPY=0 forces the
+    staged three-stream pipeline on the same buffers.  Both must equal the device-pointer call.  Ragged
+    size, and a second call on a view that starts in the middle of the pinned allocation."""
+    from modarith_b200.rfc7748 import rfc7748
+    n = 70000 + 13
+    k, u = util.random_bytes(21, n, nb), util.random_bytes(22, n, nb)
+    want = _gpu(curve, k, u)
+    hk, hu = torch.from_numpy(k).pin_memory(), torch.from_numpy(u).pin_memory()
+    hv = torch.zeros((n, nb), dtype=torch.uint8).pin_memory()
+    rfc7748(curve, hk, hu, hv)
+    assert np.array_equal(hv.numpy(), want)
+    hv.zero_()
+    rfc7748(curve, hk[1001:], hu[1001:], hv[1001:])
+    assert np.array_equal(hv.numpy()[1001:], want[1001:]) and not hv.numpy()[:1001].any()
+    monkeypatch.setenv("MAB_HOST_ZEROCOPY", "0")
+    hv.zero_()
+    rfc7748(curve, hk, hu, hv)
+    assert np.array_equal(hv.numpy(), want)
+
+
 def test_cross_check_openssl():
     """Independent implementation (OpenSSL through `cryptography`), canonical inputs only."""
     x = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.x25519")
