@@ -5104,6 +5104,11 @@ struct F_SECP256K1 {
 #endif
   }
 
+  // no spare bit above Nbits in this plan: the product-operand forms are the general ones
+  static constexpr bool TIGHT = false;
+  static MAB_DEV void add_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { add(r, a, b); }
+  static MAB_DEV void sub_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { sub(r, a, b); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[8], const uint32_t (&b)[8]) {
 #ifndef MAB_HOSTSIM

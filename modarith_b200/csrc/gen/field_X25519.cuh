@@ -2,13 +2,15 @@
 // Command line : python -m modarith_b200.gen.pseudo_sm100 X25519
 // modulus X25519 = 0x7fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffed
 // plan PseudoMersenne: 8 saturated 32-bit limbs; stored values < 2^256; R = 2^0
-//   mul   :  72 IMAD.WIDE   2 IMAD  ~ 32 ALU-pipe ops
-//   sqr   :  44 IMAD.WIDE   2 IMAD  ~ 51 ALU-pipe ops
+//   mul   :  72 IMAD.WIDE   1 IMAD  ~ 33 ALU-pipe ops
+//   sqr   :  44 IMAD.WIDE   1 IMAD  ~ 52 ALU-pipe ops
 //   mli   :   9 IMAD.WIDE   1 IMAD  ~ 16 ALU-pipe ops
 //   mla   :   9 IMAD.WIDE   1 IMAD  ~ 17 ALU-pipe ops
 //   add   :   0 IMAD.WIDE   2 IMAD  ~ 17 ALU-pipe ops
 //   sub   :   0 IMAD.WIDE   0 IMAD  ~ 21 ALU-pipe ops
 //   canon :   0 IMAD.WIDE   0 IMAD  ~ 67 ALU-pipe ops
+//   add_tt :   0 IMAD.WIDE   1 IMAD  ~  9 ALU-pipe ops
+//   sub_tt :   0 IMAD.WIDE   0 IMAD  ~ 18 ALU-pipe ops
 //   modpro: 251 squarings + 13 multiplies (exponent (p-1-2^k)/2^(k+1), k=2)
 #pragma once
 #include "mab_common.cuh"
@@ -201,24 +203,24 @@ struct F_X25519 {
         "addc.cc.u32 t62, t46, t54;\n\t"
         "addc.cc.u32 t63, t47, t55;\n\t"
         "addc.u32 t64, t48, t56;\n\t"
-        "mad.lo.cc.u32 t65, t64, 0x26, t40;\n\t"
-        "addc.cc.u32 t66, t57, 0x0;\n\t"
-        "addc.cc.u32 t67, t58, 0x0;\n\t"
-        "addc.cc.u32 t68, t59, 0x0;\n\t"
-        "addc.cc.u32 t69, t60, 0x0;\n\t"
-        "addc.cc.u32 t70, t61, 0x0;\n\t"
-        "addc.cc.u32 t71, t62, 0x0;\n\t"
-        "addc.cc.u32 t72, t63, 0x0;\n\t"
-        "addc.u32 t73, 0x0, 0x0;\n\t"
-        "mad.lo.u32 t74, t73, 0x26, t65;\n\t"
-        "mov.u32 %0, t74;\n\t"
-        "mov.u32 %1, t66;\n\t"
-        "mov.u32 %2, t67;\n\t"
-        "mov.u32 %3, t68;\n\t"
-        "mov.u32 %4, t69;\n\t"
-        "mov.u32 %5, t70;\n\t"
-        "mov.u32 %6, t71;\n\t"
-        "mov.u32 %7, t72;\n\t"
+        "shf.l.wrap.b32 t65, t63, t64, 1;\n\t"
+        "and.b32 t66, t63, 0x7fffffff;\n\t"
+        "mad.lo.cc.u32 t67, t65, 0x13, t40;\n\t"
+        "addc.cc.u32 t68, t57, 0x0;\n\t"
+        "addc.cc.u32 t69, t58, 0x0;\n\t"
+        "addc.cc.u32 t70, t59, 0x0;\n\t"
+        "addc.cc.u32 t71, t60, 0x0;\n\t"
+        "addc.cc.u32 t72, t61, 0x0;\n\t"
+        "addc.cc.u32 t73, t62, 0x0;\n\t"
+        "addc.u32 t74, t66, 0x0;\n\t"
+        "mov.u32 %0, t67;\n\t"
+        "mov.u32 %1, t68;\n\t"
+        "mov.u32 %2, t69;\n\t"
+        "mov.u32 %3, t70;\n\t"
+        "mov.u32 %4, t71;\n\t"
+        "mov.u32 %5, t72;\n\t"
+        "mov.u32 %6, t73;\n\t"
+        "mov.u32 %7, t74;\n\t"
         "}"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
@@ -409,24 +411,24 @@ struct F_X25519 {
     w_ = (uint64_t)t46 + t54 + cf_; t62 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t47 + t55 + cf_; t63 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t48 + t56 + cf_; t64 = (uint32_t)w_;
-    w_ = (uint64_t)(uint32_t)(t64 * 0x26u) + t40; t65 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t57 + 0x0u + cf_; t66 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t58 + 0x0u + cf_; t67 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t59 + 0x0u + cf_; t68 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t60 + 0x0u + cf_; t69 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t61 + 0x0u + cf_; t70 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t62 + 0x0u + cf_; t71 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t63 + 0x0u + cf_; t72 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t73 = (uint32_t)w_;
-    w_ = (uint64_t)(uint32_t)(t73 * 0x26u) + t65; t74 = (uint32_t)w_;
-    r[0] = t74;
-    r[1] = t66;
-    r[2] = t67;
-    r[3] = t68;
-    r[4] = t69;
-    r[5] = t70;
-    r[6] = t71;
-    r[7] = t72;
+    t65 = (uint32_t)(((((uint64_t)t64 << 32) | t63) << 1) >> 32);
+    t66 = (uint32_t)(t63 & 0x7fffffffu);
+    w_ = (uint64_t)(uint32_t)(t65 * 0x13u) + t40; t67 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t57 + 0x0u + cf_; t68 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t58 + 0x0u + cf_; t69 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t59 + 0x0u + cf_; t70 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t60 + 0x0u + cf_; t71 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t61 + 0x0u + cf_; t72 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t62 + 0x0u + cf_; t73 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t66 + 0x0u + cf_; t74 = (uint32_t)w_;
+    r[0] = t67;
+    r[1] = t68;
+    r[2] = t69;
+    r[3] = t70;
+    r[4] = t71;
+    r[5] = t72;
+    r[6] = t73;
+    r[7] = t74;
 #endif
   }
 
@@ -566,24 +568,24 @@ struct F_X25519 {
         "addc.cc.u32 t99, t83, t91;\n\t"
         "addc.cc.u32 t100, t84, t92;\n\t"
         "addc.u32 t101, t85, t93;\n\t"
-        "mad.lo.cc.u32 t102, t101, 0x26, t77;\n\t"
-        "addc.cc.u32 t103, t94, 0x0;\n\t"
-        "addc.cc.u32 t104, t95, 0x0;\n\t"
-        "addc.cc.u32 t105, t96, 0x0;\n\t"
-        "addc.cc.u32 t106, t97, 0x0;\n\t"
-        "addc.cc.u32 t107, t98, 0x0;\n\t"
-        "addc.cc.u32 t108, t99, 0x0;\n\t"
-        "addc.cc.u32 t109, t100, 0x0;\n\t"
-        "addc.u32 t110, 0x0, 0x0;\n\t"
-        "mad.lo.u32 t111, t110, 0x26, t102;\n\t"
-        "mov.u32 %0, t111;\n\t"
-        "mov.u32 %1, t103;\n\t"
-        "mov.u32 %2, t104;\n\t"
-        "mov.u32 %3, t105;\n\t"
-        "mov.u32 %4, t106;\n\t"
-        "mov.u32 %5, t107;\n\t"
-        "mov.u32 %6, t108;\n\t"
-        "mov.u32 %7, t109;\n\t"
+        "shf.l.wrap.b32 t102, t100, t101, 1;\n\t"
+        "and.b32 t103, t100, 0x7fffffff;\n\t"
+        "mad.lo.cc.u32 t104, t102, 0x13, t77;\n\t"
+        "addc.cc.u32 t105, t94, 0x0;\n\t"
+        "addc.cc.u32 t106, t95, 0x0;\n\t"
+        "addc.cc.u32 t107, t96, 0x0;\n\t"
+        "addc.cc.u32 t108, t97, 0x0;\n\t"
+        "addc.cc.u32 t109, t98, 0x0;\n\t"
+        "addc.cc.u32 t110, t99, 0x0;\n\t"
+        "addc.u32 t111, t103, 0x0;\n\t"
+        "mov.u32 %0, t104;\n\t"
+        "mov.u32 %1, t105;\n\t"
+        "mov.u32 %2, t106;\n\t"
+        "mov.u32 %3, t107;\n\t"
+        "mov.u32 %4, t108;\n\t"
+        "mov.u32 %5, t109;\n\t"
+        "mov.u32 %6, t110;\n\t"
+        "mov.u32 %7, t111;\n\t"
         "}"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
@@ -729,24 +731,24 @@ struct F_X25519 {
     w_ = (uint64_t)t83 + t91 + cf_; t99 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t84 + t92 + cf_; t100 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
     w_ = (uint64_t)t85 + t93 + cf_; t101 = (uint32_t)w_;
-    w_ = (uint64_t)(uint32_t)(t101 * 0x26u) + t77; t102 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t94 + 0x0u + cf_; t103 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t95 + 0x0u + cf_; t104 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t96 + 0x0u + cf_; t105 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t97 + 0x0u + cf_; t106 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t98 + 0x0u + cf_; t107 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t99 + 0x0u + cf_; t108 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)t100 + 0x0u + cf_; t109 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
-    w_ = (uint64_t)0x0u + 0x0u + cf_; t110 = (uint32_t)w_;
-    w_ = (uint64_t)(uint32_t)(t110 * 0x26u) + t102; t111 = (uint32_t)w_;
-    r[0] = t111;
-    r[1] = t103;
-    r[2] = t104;
-    r[3] = t105;
-    r[4] = t106;
-    r[5] = t107;
-    r[6] = t108;
-    r[7] = t109;
+    t102 = (uint32_t)(((((uint64_t)t101 << 32) | t100) << 1) >> 32);
+    t103 = (uint32_t)(t100 & 0x7fffffffu);
+    w_ = (uint64_t)(uint32_t)(t102 * 0x13u) + t77; t104 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t94 + 0x0u + cf_; t105 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t95 + 0x0u + cf_; t106 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t96 + 0x0u + cf_; t107 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t97 + 0x0u + cf_; t108 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t98 + 0x0u + cf_; t109 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t99 + 0x0u + cf_; t110 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)t103 + 0x0u + cf_; t111 = (uint32_t)w_;
+    r[0] = t104;
+    r[1] = t105;
+    r[2] = t106;
+    r[3] = t107;
+    r[4] = t108;
+    r[5] = t109;
+    r[6] = t110;
+    r[7] = t111;
 #endif
   }
 
@@ -1140,6 +1142,156 @@ struct F_X25519 {
     t19 = (uint32_t)(t18 & 0x26u);
     w_ = (uint64_t)t10 - t19; t20 = (uint32_t)w_;
     r[0] = t20;
+    r[1] = t11;
+    r[2] = t12;
+    r[3] = t13;
+    r[4] = t14;
+    r[5] = t15;
+    r[6] = t16;
+    r[7] = t17;
+#endif
+  }
+
+  // Products (mul, sqr) of this field stay below 2^255 + 19*2^13 whatever their operands; add_tt / sub_tt
+  // are modadd / modsub for two such values (no second wrap to handle); their results are ordinary
+  // stored values (< 2^256), which every function accepts.
+  static constexpr bool TIGHT = true;
+  static MAB_DEV void add_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#ifndef MAB_HOSTSIM
+    asm("{\n\t"
+        ".reg .u32 t<10>;\n\t"
+        "add.cc.u32 t0, %8, %16;\n\t"
+        "addc.cc.u32 t1, %9, %17;\n\t"
+        "addc.cc.u32 t2, %10, %18;\n\t"
+        "addc.cc.u32 t3, %11, %19;\n\t"
+        "addc.cc.u32 t4, %12, %20;\n\t"
+        "addc.cc.u32 t5, %13, %21;\n\t"
+        "addc.cc.u32 t6, %14, %22;\n\t"
+        "addc.cc.u32 t7, %15, %23;\n\t"
+        "addc.u32 t8, 0x0, 0x0;\n\t"
+        "mad.lo.u32 t9, t8, 0x26, t0;\n\t"
+        "mov.u32 %0, t9;\n\t"
+        "mov.u32 %1, t1;\n\t"
+        "mov.u32 %2, t2;\n\t"
+        "mov.u32 %3, t3;\n\t"
+        "mov.u32 %4, t4;\n\t"
+        "mov.u32 %5, t5;\n\t"
+        "mov.u32 %6, t6;\n\t"
+        "mov.u32 %7, t7;\n\t"
+        "}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    const uint32_t a_0_i = a[0];
+    const uint32_t a_1_i = a[1];
+    const uint32_t a_2_i = a[2];
+    const uint32_t a_3_i = a[3];
+    const uint32_t a_4_i = a[4];
+    const uint32_t a_5_i = a[5];
+    const uint32_t a_6_i = a[6];
+    const uint32_t a_7_i = a[7];
+    const uint32_t b_0_i = b[0];
+    const uint32_t b_1_i = b[1];
+    const uint32_t b_2_i = b[2];
+    const uint32_t b_3_i = b[3];
+    const uint32_t b_4_i = b[4];
+    const uint32_t b_5_i = b[5];
+    const uint32_t b_6_i = b[6];
+    const uint32_t b_7_i = b[7];
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7, t8, t9;
+    uint64_t w_; uint32_t cf_ = 0; (void)cf_; (void)w_;
+    w_ = (uint64_t)a_0_i + b_0_i; t0 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_1_i + b_1_i + cf_; t1 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_2_i + b_2_i + cf_; t2 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_3_i + b_3_i + cf_; t3 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_4_i + b_4_i + cf_; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_5_i + b_5_i + cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_6_i + b_6_i + cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)a_7_i + b_7_i + cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 32);
+    w_ = (uint64_t)0x0u + 0x0u + cf_; t8 = (uint32_t)w_;
+    w_ = (uint64_t)(uint32_t)(t8 * 0x26u) + t0; t9 = (uint32_t)w_;
+    r[0] = t9;
+    r[1] = t1;
+    r[2] = t2;
+    r[3] = t3;
+    r[4] = t4;
+    r[5] = t5;
+    r[6] = t6;
+    r[7] = t7;
+#endif
+  }
+
+  static MAB_DEV void sub_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#ifndef MAB_HOSTSIM
+    asm("{\n\t"
+        ".reg .u32 t<18>;\n\t"
+        "sub.cc.u32 t0, %8, %16;\n\t"
+        "subc.cc.u32 t1, %9, %17;\n\t"
+        "subc.cc.u32 t2, %10, %18;\n\t"
+        "subc.cc.u32 t3, %11, %19;\n\t"
+        "subc.cc.u32 t4, %12, %20;\n\t"
+        "subc.cc.u32 t5, %13, %21;\n\t"
+        "subc.cc.u32 t6, %14, %22;\n\t"
+        "subc.cc.u32 t7, %15, %23;\n\t"
+        "subc.u32 t8, 0x0, 0x0;\n\t"
+        "and.b32 t9, t8, 0x26;\n\t"
+        "sub.cc.u32 t10, t0, t9;\n\t"
+        "subc.cc.u32 t11, t1, 0x0;\n\t"
+        "subc.cc.u32 t12, t2, 0x0;\n\t"
+        "subc.cc.u32 t13, t3, 0x0;\n\t"
+        "subc.cc.u32 t14, t4, 0x0;\n\t"
+        "subc.cc.u32 t15, t5, 0x0;\n\t"
+        "subc.cc.u32 t16, t6, 0x0;\n\t"
+        "subc.u32 t17, t7, 0x0;\n\t"
+        "mov.u32 %0, t10;\n\t"
+        "mov.u32 %1, t11;\n\t"
+        "mov.u32 %2, t12;\n\t"
+        "mov.u32 %3, t13;\n\t"
+        "mov.u32 %4, t14;\n\t"
+        "mov.u32 %5, t15;\n\t"
+        "mov.u32 %6, t16;\n\t"
+        "mov.u32 %7, t17;\n\t"
+        "}"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    const uint32_t a_0_i = a[0];
+    const uint32_t a_1_i = a[1];
+    const uint32_t a_2_i = a[2];
+    const uint32_t a_3_i = a[3];
+    const uint32_t a_4_i = a[4];
+    const uint32_t a_5_i = a[5];
+    const uint32_t a_6_i = a[6];
+    const uint32_t a_7_i = a[7];
+    const uint32_t b_0_i = b[0];
+    const uint32_t b_1_i = b[1];
+    const uint32_t b_2_i = b[2];
+    const uint32_t b_3_i = b[3];
+    const uint32_t b_4_i = b[4];
+    const uint32_t b_5_i = b[5];
+    const uint32_t b_6_i = b[6];
+    const uint32_t b_7_i = b[7];
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17;
+    uint64_t w_; uint32_t cf_ = 0; (void)cf_; (void)w_;
+    w_ = (uint64_t)a_0_i - b_0_i; t0 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_1_i - b_1_i - cf_; t1 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_2_i - b_2_i - cf_; t2 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_3_i - b_3_i - cf_; t3 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_4_i - b_4_i - cf_; t4 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_5_i - b_5_i - cf_; t5 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_6_i - b_6_i - cf_; t6 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)a_7_i - b_7_i - cf_; t7 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)0x0u - 0x0u - cf_; t8 = (uint32_t)w_;
+    t9 = (uint32_t)(t8 & 0x26u);
+    w_ = (uint64_t)t0 - t9; t10 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t1 - 0x0u - cf_; t11 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t2 - 0x0u - cf_; t12 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t3 - 0x0u - cf_; t13 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t4 - 0x0u - cf_; t14 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t5 - 0x0u - cf_; t15 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t6 - 0x0u - cf_; t16 = (uint32_t)w_; cf_ = (uint32_t)(w_ >> 63);
+    w_ = (uint64_t)t7 - 0x0u - cf_; t17 = (uint32_t)w_;
+    r[0] = t10;
     r[1] = t11;
     r[2] = t12;
     r[3] = t13;

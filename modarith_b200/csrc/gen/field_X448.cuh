@@ -2512,6 +2512,11 @@ struct F_X448 {
 #endif
   }
 
+  // no spare bit above Nbits in this plan: the product-operand forms are the general ones
+  static constexpr bool TIGHT = false;
+  static MAB_DEV void add_tt(uint32_t (&r)[14], const uint32_t (&a)[14], const uint32_t (&b)[14]) { add(r, a, b); }
+  static MAB_DEV void sub_tt(uint32_t (&r)[14], const uint32_t (&a)[14], const uint32_t (&b)[14]) { sub(r, a, b); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[14], const uint32_t (&b)[14]) {
 #ifndef MAB_HOSTSIM

@@ -71,6 +71,8 @@ template <class F> struct Rfc7748 {
       for (int j = 0; j < L; j++) { stash[j * pitch] = k[j]; stash[(L + j) * pitch] = x1[j]; }
     }
 
+    // Every addition and subtraction of the step takes two products (or the initial 1, 0, u < 2^Nbits):
+    // where the field keeps products below 2^Nbits + c*2^13 (F::TIGHT) the _tt forms apply.
     uint32_t swap = 0;
     MAB_NOUNROLL
     for (int w = L - 1; w >= 0; w--) {           // rfc7748.c:186-221, bits Nbits-1 .. 0
@@ -92,10 +94,10 @@ template <class F> struct Rfc7748 {
         swap = kt;
 
         uint32_t A[L], B[L], C[L], D[L], AA[L], BB[L];
-        F::add(A, x2, z2);                         // A = x2+z2
-        F::sub(B, x2, z2);                         // B = x2-z2
-        F::add(C, x3, z3);                         // C = x3+z3
-        F::sub(D, x3, z3);                         // D = x3-z3
+        F::add_tt(A, x2, z2);                         // A = x2+z2
+        F::sub_tt(B, x2, z2);                         // B = x2-z2
+        F::add_tt(C, x3, z3);                         // C = x3+z3
+        F::sub_tt(D, x3, z3);                         // D = x3-z3
 #pragma unroll
         for (int j = 0; j < L; j++) AA[j] = (A[j] & ~m) | (C[j] & m);
 #pragma unroll
@@ -104,8 +106,8 @@ template <class F> struct Rfc7748 {
         F::mul(C, C, B);                           // CB (or DA)
         F::sqr(A, AA);                             // AA
         F::sqr(B, BB);                             // BB
-        F::add(x3, D, C);
-        F::sub(z3, D, C);
+        F::add_tt(x3, D, C);
+        F::sub_tt(z3, D, C);
         F::sqr(x3, x3);                            // x3 = (DA+CB)^2
         F::sqr(z3, z3);
         if (stash) {
@@ -117,7 +119,7 @@ template <class F> struct Rfc7748 {
           F::mul(z3, z3, x1);
         }
         F::mul(x2, A, B);                          // x2 = AA*BB
-        F::sub(B, A, B);                           // E = AA-BB
+        F::sub_tt(B, A, B);                           // E = AA-BB
         F::mla(z2, B, F::A24, A);                  // a24*E + AA  (modmli + modadd fused)
         F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
       }
@@ -131,12 +133,12 @@ template <class F> struct Rfc7748 {
 #pragma unroll 1
     for (int i = 0; i < MAB_TAIL_DOUBLINGS(F); i++) {   // bits COF-1..0 are 0: x2,z2 <- double(x2,z2)
       uint32_t A[L], B[L];
-      F::add(A, x2, z2);
-      F::sub(B, x2, z2);
+      F::add_tt(A, x2, z2);
+      F::sub_tt(B, x2, z2);
       F::sqr(A, A);                              // AA
       F::sqr(B, B);                              // BB
       F::mul(x2, A, B);                          // x2 = AA*BB
-      F::sub(B, A, B);                           // E
+      F::sub_tt(B, A, B);                           // E
       F::mla(z2, B, F::A24, A);
       F::mul(z2, z2, B);                         // z2 = E*(AA+a24*E)
     }

@@ -55,7 +55,7 @@ def emit_field_header(plan: Plan) -> str:
     out.append("// plan %s: %d saturated 32-bit limbs; stored values < %s; R = 2^%d\n" % (
         type(plan).__name__, L, "p" if plan.bound == P.p else "2^%d" % (32 * L),
         plan.R.bit_length() - 1))
-    for k in ("mul", "sqr", "mli", "mla", "add", "sub", "canon"):
+    for k in ("mul", "sqr", "mli", "mla", "add", "sub", "canon") + (("add_tt", "sub_tt") if plan.tight else ()):
         w, i, a = blocks[k].stats()
         out.append("//   %-5s : %3d IMAD.WIDE  %2d IMAD  ~%3d ALU-pipe ops\n" % (k, w, i, a))
     out.append("//   modpro: %d squarings + %d multiplies (exponent (p-1-2^k)/2^(k+1), k=%d)\n" %
@@ -96,6 +96,18 @@ def emit_field_header(plan: Plan) -> str:
     out.append(_block_fn(plan, "add", blocks["add"], "%s, %s, %s" % (r, a, b)))
     out.append("  // n = a-b (pseudo.py:307-326)\n")
     out.append(_block_fn(plan, "sub", blocks["sub"], "%s, %s, %s" % (r, a, b)))
+    if plan.tight:
+        out.append("  // Products (mul, sqr) of this field stay below 2^%d + %d*2^13 whatever their operands; add_tt / sub_tt\n"
+                   "  // are modadd / modsub for two such values (no second wrap to handle); their results are ordinary\n"
+                   "  // stored values (< 2^%d), which every function accepts.\n" % (P.nbits, (1 << P.nbits) - P.p, 32 * L))
+        out.append("  static constexpr bool TIGHT = true;\n")
+        out.append(_block_fn(plan, "add_tt", blocks["add_tt"], "%s, %s, %s" % (r, a, b)))
+        out.append(_block_fn(plan, "sub_tt", blocks["sub_tt"], "%s, %s, %s" % (r, a, b)))
+    else:
+        out.append("  // no spare bit above Nbits in this plan: the product-operand forms are the general ones\n")
+        out.append("  static constexpr bool TIGHT = false;\n")
+        out.append("  static MAB_DEV void add_tt(%s, %s, %s) { add(r, a, b); }\n" % (r, a, b))
+        out.append("  static MAB_DEV void sub_tt(%s, %s, %s) { sub(r, a, b); }\n\n" % (r, a, b))
     out.append("  // n = -b (pseudo.py:329-348)\n")
     out.append(_block_fn(plan, "neg", blocks["neg"], "%s, %s" % (r, b)))
     out.append("  // canonical residue of a stored value; returns 1 iff it was already < p\n"

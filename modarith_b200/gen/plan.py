@@ -52,6 +52,7 @@ class Plan:
     # the last product chain, see Asm.link_cc; MAB_LINK=0 switches it off (experiment)
     link_products = False
     family = "?"
+    tight = None            # exclusive bound of mul/sqr outputs when it is below 2^(32L) (see PseudoMersenne)
 
     def __init__(self, prime: Prime):
         self.P = prime
@@ -83,6 +84,9 @@ class Plan:
             "neg": self.build_sub(neg=True),
             "canon": self.build_canon(),
         }
+        if self.tight:
+            self.blocks["add_tt"] = self.build_add_tt()
+            self.blocks["sub_tt"] = self.build_sub_tt()
         return self.blocks
 
     def _io(self, asm, ins, out="r"):
@@ -190,6 +194,25 @@ class Plan:
             assert r < B and r % p == (-x) % p, ("neg", hex(x))
             r, e = self.run("canon", a=ax)
             assert r == x % p and e["lt"] == (1 if x < p else 0), ("canon", hex(x))
+        if self.tight:
+            # mul/sqr land below the tight bound for ANY stored operands; add_tt/sub_tt are exact on tight operands
+            T = self.tight
+            for x, y in zip(xs, ys):
+                r, _ = self.run("mul", a=words(x, L), b=words(y, L))
+                assert r < T, ("mul not tight", hex(x), hex(y))
+                r, _ = self.run("sqr", a=words(x, L))
+                assert r < T, ("sqr not tight", hex(x))
+            edge = [0, 1, 2, 37, 38, 39, p - 1, p, p + 1, T - 1, T - 2, T - 38, T - 39, (1 << (32 * L - 1)) - 1,
+                    1 << (32 * L - 1), (1 << (32 * L - 1)) + 1, M32, 1 << 32, (1 << 32) - 38]
+            ts = [e for e in edge if 0 <= e < T]
+            pairs = [(a, b) for a in ts for b in ts]
+            while len(pairs) < len(ts) ** 2 + trials:
+                pairs.append((rng.randrange(T), rng.randrange(T)))
+            for x, y in pairs:
+                r, _ = self.run("add_tt", a=words(x, L), b=words(y, L))
+                assert r < B and r % p == (x + y) % p, ("add_tt", hex(x), hex(y))
+                r, _ = self.run("sub_tt", a=words(x, L), b=words(y, L))
+                assert r < B and r % p == (x - y) % p, ("sub_tt", hex(x), hex(y))
         return True
 
     # -- shared small pieces ------------------------------------------------
@@ -224,6 +247,13 @@ class PseudoMersenne(Plan):
         self.fold = self.c << self.xs            # 2^(32L) == fold (mod p); cf. mm=m*2^xcess, pseudo.py:1594-1596
         assert self.fold * (self.fold + 2) < (1 << 32), "fold constant too large for this plan"
         assert self.bound <= 2 * self.p + self.fold + 1
+        # A spare bit above Nbits (2^255-19 in 8 words) lets products be folded at bit Nbits instead of at
+        # bit 32L for the same instruction count (_fold_top): they then stay below 2^Nbits + c*2^13, and
+        # sums / differences of two such values need no second wrap (add_tt 10 instructions instead of
+        # 20, sub_tt 18 instead of 21).  MAB_TIGHT=0 switches it off (experiment).
+        if self.xs >= 1 and os.environ.get("MAB_TIGHT", "1") != "0" and os.environ.get("MAB_FOLD", "split") == "split":
+            self.tight = (1 << n) + self.c * (1 << 13)
+            assert 2 * self.tight < (1 << (32 * self.L)) + (1 << 32) - self.fold      # add_tt: wrapped sum + fold fits word 0
 
     def _fold_carry(self, asm, r, c, wide=False):
         """r (L words) += c * fold, where c*2^(32L) was dropped.  c is a register.
@@ -251,6 +281,52 @@ class PseudoMersenne(Plan):
             return [f, g] + o[2:]
         asm.madlo(f, c2, self.fold, o[0])
         return [f] + o[1:]
+
+    def _fold_top(self, asm, r, top):
+        """r (L words) + top * 2^(32L)  ->  L words below 2^Nbits + c * 2^13: everything at or above bit
+        Nbits (`top` and the xs spare bits of the last word) is multiplied by c and added at the bottom.
+        Same cost as _fold_carry, and no second wrap can occur."""
+        L, xs = self.L, self.xs
+        h = asm.tmp()
+        asm.shfl(h, r[L - 1], top, xs)                    # (top : r[L-1]) << xs, high word = bits >= Nbits
+        last = asm.tmp()
+        asm.logic("and", last, r[L - 1], M32 >> xs)
+        o = asm.tmp(L)
+        asm.madlo(o[0], h, self.c, r[0], cout=True)
+        for k in range(1, L - 1):
+            asm.add(o[k], r[k], 0, cin=True, cout=True)
+        asm.add(o[L - 1], last, 0, cin=True)
+        return o
+
+    def build_add_tt(self):
+        """a + b for a, b below the tight bound: the sum wraps past 2^(32L) at most once, and when it does
+        the wrapped value is so small that adding the fold constant cannot carry out of word 0."""
+        asm = Asm(self.name + ".add_tt")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        s = asm.tmp(L)
+        c = asm.tmp()
+        asm.add_chain(s, a, b, carry_to=(c, 0))
+        f = asm.tmp()
+        asm.madlo(f, c, self.fold, s[0])
+        self._outs(asm, [f] + s[1:])
+        return asm
+
+    def build_sub_tt(self):
+        """a - b for a, b below the tight bound: after a borrow the difference is at least
+        2^(32L) - tight > fold, so taking the fold constant off cannot borrow a second time."""
+        asm = Asm(self.name + ".sub_tt")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)
+        f = asm.tmp()
+        asm.logic("and", f, m, self.fold)
+        e = asm.tmp(L)
+        asm.sub_chain(e, d, [f] + [0] * (L - 1))
+        self._outs(asm, e)
+        return asm
 
     def reduce_wide(self, asm, T):
         """2L words -> L words: lo + fold*hi (second_pass of pseudo.py:557-611 restated for a
@@ -321,7 +397,7 @@ class PseudoMersenne(Plan):
         for k in range(1, L):
             asm.add(res[k], r[k], o[k], cin=(k > 1), cout=True)
         asm.add(top, ce, o[L], cin=True, cout=False)
-        return self._fold_carry(asm, res, top)
+        return self._fold_top(asm, res, top) if self.tight else self._fold_carry(asm, res, top)
 
     def build_mul(self):
         if os.environ.get("MAB_FOLD", "split") != "split":
