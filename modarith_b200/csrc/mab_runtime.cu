@@ -144,6 +144,35 @@ int mab_chunk_counter(cudaStream_t stream, unsigned long long** out) {
   return 0;
 }
 
+// ---- stream-ordered scratch pool (table slices of the scalar multiplication kernels) -------------------
+static cudaMemPool_t g_pool[MAB_WS_MAXDEV];
+static bool g_pool_ready[MAB_WS_MAXDEV];
+static std::mutex g_pool_mutex;
+
+int mab_scratch_alloc(void** out, size_t bytes, cudaStream_t stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= MAB_WS_MAXDEV) return MAB_ERR_BADARG;
+  {
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    if (!g_pool_ready[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if ((e = cudaMemPoolCreate(&g_pool[dev], &props)) != cudaSuccess) return (int)e;
+      unsigned long long keep = ~0ull;
+      if ((e = cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return (int)e;
+      g_pool_ready[dev] = true;
+    }
+  }
+  return (int)cudaMallocFromPoolAsync(out, bytes, g_pool[dev], stream);
+}
+
+int mab_scratch_free(void* p, cudaStream_t stream) { return (int)cudaFreeAsync(p, stream); }
+
 static const char* kVersion = "modarith_b200 0.1 (sm_100a)";
 
 // W(modmul)=L^2, W(modsqr)=L(L+1)/2, W(modmli)=L with L=ceil(Nbits/32); chains
@@ -182,6 +211,14 @@ const char* mab_error_string(int code) {
 }
 
 void mab_release_workspaces(void) {
+  {
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    for (int d = 0; d < MAB_WS_MAXDEV; d++)
+      if (g_pool_ready[d]) {
+        cudaMemPoolDestroy(g_pool[d]);
+        g_pool_ready[d] = false;
+      }
+  }
   for (int d = 0; d < MAB_WS_MAXDEV; d++) {
     std::lock_guard<std::mutex> g(g_ws_mutex[d]);
     MabWorkspace* ws = &g_ws[d];

@@ -18,3 +18,7 @@ void mab_host_workspace_release(MabWorkspace* ws);
 // are handed out round-robin and cleared on `stream` ahead of the launch, so launches that overlap on
 // different streams never share one.
 int mab_chunk_counter(cudaStream_t stream, unsigned long long** out);
+// Stream-ordered scratch memory from a pool the library owns (one per device, created on first use, keeps
+// what is freed so that repeated calls do not reach the driver; destroyed by mab_release_workspaces).
+int mab_scratch_alloc(void** out, size_t bytes, cudaStream_t stream);
+int mab_scratch_free(void* p, cudaStream_t stream);
