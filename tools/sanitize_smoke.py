@@ -48,5 +48,8 @@ for curve, gx, gy in (("NIST256", PRIMES["NIST256"].wgx, PRIMES["NIST256"].wgy),
     xo, yo = ecnmul(curve, e, x, y)
     xo2, yo2 = ecnmul(curve, e, x, y)
     assert torch.equal(xo, xo2) and torch.equal(yo, yo2)
+    from modarith_b200.ecn import ecnmul2  # noqa: E402
+    f = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    ecnmul2(curve, e, x, y, f, xo, yo)
 torch.cuda.synchronize()
 print("sanitize smoke done")
