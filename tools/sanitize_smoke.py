@@ -21,8 +21,10 @@ for curve, nb in (("X25519", 32), ("X448", 56)):
     u = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
     a = rfc7748(curve, k, u)
     b = rfc7748(curve, k, u, validate=True)
-    h = rfc7748(curve, k.cpu().numpy(), u.cpu().numpy())
+    h = rfc7748(curve, k.cpu().numpy(), u.cpu().numpy())                 # pageable host arrays: staged pipeline
     assert (a.cpu().numpy() == h).all()
+    z = rfc7748(curve, k.cpu().pin_memory(), u.cpu().pin_memory())        # pinned: the kernel reads / writes host memory
+    assert (a.cpu() == z).all()
 for name in ("X25519", "X448", "NIST256"):
     F = Field(name)
     n = 131
