@@ -1156,7 +1156,17 @@ struct F_X25519 {
   // are modadd / modsub for two such values (no second wrap to handle); their results are ordinary
   // stored values (< 2^256), which every function accepts.
   static constexpr bool TIGHT = true;
+#ifdef MAB_HOSTSIM
+  static inline bool sim_tight(const uint32_t (&a)[8]) {   // a < 2^255 + 19*2^13 ?
+    static const uint32_t t[8] = {0x00026000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x00000000u, 0x80000000u};
+    for (int i = 7; i >= 0; i--) { if (a[i] != t[i]) return a[i] < t[i]; }
+    return false;
+  }
+#endif
   static MAB_DEV void add_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#ifdef MAB_HOSTSIM
+    MAB_SIM_REQUIRE(sim_tight(a) && sim_tight(b), "X25519.add_tt operands below the product bound");
+#endif
 #ifndef MAB_HOSTSIM
     asm("{\n\t"
         ".reg .u32 t<10>;\n\t"
@@ -1222,6 +1232,9 @@ struct F_X25519 {
   }
 
   static MAB_DEV void sub_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#ifdef MAB_HOSTSIM
+    MAB_SIM_REQUIRE(sim_tight(a) && sim_tight(b), "X25519.sub_tt operands below the product bound");
+#endif
 #ifndef MAB_HOSTSIM
     asm("{\n\t"
         ".reg .u32 t<18>;\n\t"

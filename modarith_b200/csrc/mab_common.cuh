@@ -11,8 +11,12 @@
 #include <stddef.h>
 
 #ifdef MAB_HOSTSIM
+#include <stdio.h>
+#include <stdlib.h>
 #define MAB_DEV inline
 #define MAB_NOUNROLL
+// call-site invariants of the generated code are CHECKED in the host simulation (the device build trusts them)
+#define MAB_SIM_REQUIRE(cond, what) do { if (!(cond)) { fprintf(stderr, "hostsim: violated precondition: %s\n", what); abort(); } } while (0)
 struct uint4 { uint32_t x, y, z, w; };           // the 16-byte vector type of the device build
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = {x, y, z, w}; return v; }
 static inline uint32_t mab_sim_prmt(uint32_t a, uint32_t b, uint32_t sel) {

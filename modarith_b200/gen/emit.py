@@ -101,8 +101,16 @@ def emit_field_header(plan: Plan) -> str:
                    "  // are modadd / modsub for two such values (no second wrap to handle); their results are ordinary\n"
                    "  // stored values (< 2^%d), which every function accepts.\n" % (P.nbits, (1 << P.nbits) - P.p, 32 * L))
         out.append("  static constexpr bool TIGHT = true;\n")
-        out.append(_block_fn(plan, "add_tt", blocks["add_tt"], "%s, %s, %s" % (r, a, b)))
-        out.append(_block_fn(plan, "sub_tt", blocks["sub_tt"], "%s, %s, %s" % (r, a, b)))
+        tw = words(plan.tight, L)
+        out.append("#ifdef MAB_HOSTSIM\n  static inline bool sim_tight(%s) {   // a < 2^%d + %d*2^13 ?\n"
+                   "    static const uint32_t t[%d] = {%s};\n"
+                   "    for (int i = %d; i >= 0; i--) { if (a[i] != t[i]) return a[i] < t[i]; }\n    return false;\n  }\n#endif\n"
+                   % (_arr("a", L, True), P.nbits, (1 << P.nbits) - P.p, L, ", ".join("0x%08xu" % w for w in tw), L - 1))
+        chk = ('#ifdef MAB_HOSTSIM\n    MAB_SIM_REQUIRE(sim_tight(a) && sim_tight(b), "%s.%s operands below the product bound");\n#endif\n')
+        for fn in ("add_tt", "sub_tt"):
+            body = _block_fn(plan, fn, blocks[fn], "%s, %s, %s" % (r, a, b))
+            head, rest = body.split("{\n", 1)
+            out.append(head + "{\n" + chk % (P.name, fn) + rest)
     else:
         out.append("  // no spare bit above Nbits in this plan: the product-operand forms are the general ones\n")
         out.append("  static constexpr bool TIGHT = false;\n")

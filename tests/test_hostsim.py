@@ -93,6 +93,30 @@ def test_ladder_random_vs_oracle(hostsim, curve):
         assert out[i].tobytes() == rfc7748(curve, k[i].tobytes(), u[i].tobytes())
 
 
+@pytest.mark.parametrize("curve", CURVES)
+def test_ladder_saturated_word_patterns(hostsim, curve):
+    """Scalars and u-coordinates made of all-ones / all-zero / single-bit words: the operands most likely to
+    break a bound the ladder step relies on (the 2^255-19 step adds and subtracts products with add_tt /
+    sub_tt, whose preconditions the host simulation checks on every call and aborts on)."""
+    nb = PRIMES[curve].nbytes
+    rng = np.random.default_rng(255)
+    pats = np.array([0x00, 0xff, 0x80, 0x01, 0x7f, 0xfe], dtype=np.uint8)
+    n = 48
+    k = np.repeat(pats[rng.integers(0, len(pats), (n, nb // 4))], 4, axis=1).astype(np.uint8)
+    u = np.repeat(pats[rng.integers(0, len(pats), (n, nb // 4))], 4, axis=1).astype(np.uint8)
+    k[:4] = 0xff
+    u[:2] = 0xff
+    u[2:4] = 0
+    p = PRIMES[curve].p
+    for i, v in enumerate((p - 1, p + 1, 2 * p - 1 if curve == "X25519" else p - 2, (1 << (8 * nb - 1)) - 1)):
+        u[4 + i] = np.frombuffer((v % (1 << (8 * nb))).to_bytes(nb, "little"), dtype=np.uint8)
+    out = np.zeros_like(k)
+    getattr(hostsim, "sim_%s_rfc7748_batch" % curve)(k.ctypes.data_as(ctypes.c_void_p), u.ctypes.data_as(ctypes.c_void_p),
+                                                      out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n))
+    for i in range(n):
+        assert out[i].tobytes() == rfc7748(curve, k[i].tobytes(), u[i].tobytes()), i
+
+
 @pytest.mark.parametrize("name", list(PRIMES))
 def test_field_golden(hostsim, golden_field, name):
     g = golden_field[name]
