@@ -34,16 +34,16 @@ template <class F> struct Edwards {
     F::mul(D, P.y, Q.y);
     F::mul(E, C, D);
     F::mul(E, E, dd);
-    F::sub(Ff, B, E);
-    F::add(Gg, B, E);
-    F::add(B, P.x, P.y);
-    F::add(E, Q.x, Q.y);
+    F::sub_tt(Ff, B, E);
+    F::add_tt(Gg, B, E);
+    F::add_tt(B, P.x, P.y);
+    F::add(E, Q.x, Q.y);                         // Q is not necessarily a product: general form
     F::mul(B, B, E);
-    F::sub(B, B, C);
-    F::sub(B, B, D);
+    F::sub_tt(B, B, C);
+    F::sub(B, B, D);                             // B is a difference by now: general form
     F::mul(B, B, Ff);
     F::mul(P.x, B, A);                           // X3 = A*F*((X1+Y1)(X2+Y2)-C-D)
-    F::add(D, D, C);                             // D - a*C with a = -1
+    F::add_tt(D, D, C);                          // D - a*C with a = -1
     F::mul(D, D, A);
     F::mul(P.y, D, Gg);                          // Y3 = A*G*(D+C)
     F::mul(P.z, Ff, Gg);                         // Z3 = F*G
@@ -52,18 +52,18 @@ template <class F> struct Edwards {
   // P <- 2P  (a = -1): 3M + 4S
   static MAB_DEV void dbl(Pt& P) {
     uint32_t B[L], C[L], D[L], H[L], Ff[L], J[L];
-    F::add(B, P.x, P.y);
+    F::add_tt(B, P.x, P.y);
     F::sqr(B, B);
     F::sqr(C, P.x);
     F::sqr(D, P.y);
     F::sqr(H, P.z);
-    F::add(H, H, H);
-    F::sub(Ff, D, C);                            // F = a*C + D = D - C
+    F::add_tt(H, H, H);
+    F::sub_tt(Ff, D, C);                         // F = a*C + D = D - C
     F::sub(J, Ff, H);                            // J = F - 2Z^2
-    F::sub(B, B, C);
+    F::sub_tt(B, B, C);
     F::sub(B, B, D);
     F::mul(P.x, B, J);                           // X3 = (B-C-D)*J
-    F::add(C, C, D);
+    F::add_tt(C, C, D);
     F::neg(C, C);                                // E - D = -C - D
     F::mul(P.y, Ff, C);                          // Y3 = F*(E-D)
     F::mul(P.z, Ff, J);                          // Z3 = F*J
@@ -83,6 +83,10 @@ template <class F> struct Edwards {
     Fd::one(one);
     F::add(V, V, one);
     const uint32_t bad = 1u - Fd::cmp(U, V);
+    if (F::TIGHT) {                                // imported words may be anything below 2^(32L): x*1, y*1 are products
+      F::mul(P.x, P.x, one);
+      F::mul(P.y, P.y, one);
+    }
     Fd::one(P.z);
     Pt O;
     inf(O);

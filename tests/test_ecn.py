@@ -134,3 +134,29 @@ def test_gpu_large_ragged_batch_is_position_independent(curve):
     assert np.array_equal(xo, x0[idx]) and np.array_equal(yo, y0[idx])
     xe, ye = _gpu(e0[:0], gx[:0], gy[:0], curve)
     assert xe.shape == (0, 32) and ye.shape == (0, 32)
+
+
+def test_hostsim_ed25519_random_points_check_operand_bounds(hostsim):
+    """Random multiples of the generator (so that the table and the accumulator see arbitrary coordinates) with
+    random and saturated scalars, single and double multiplication: the host simulation aborts if an add_tt /
+    sub_tt of the Edwards law ever receives an operand above the product bound; results against the oracle."""
+    from field_oracle import ecnmul2 as oracle_ecnmul2
+    Q = ALL_PRIMES["X25519"]
+    g = (Q.ed_gx.to_bytes(32, "big"), Q.ed_gy.to_bytes(32, "big"))
+    rng = np.random.default_rng(25519)
+    sc = [rng.integers(0, 256, 32, dtype=np.uint8).tobytes() for _ in range(10)] + [b"\xff" * 32, b"\x88" * 32, b"\x77" * 32,
+                                                                                   b"\x80" + bytes(31), bytes(31) + b"\x08"]
+    f1, f2 = hostsim.sim_ED25519_ecnmul, hostsim.sim_ED25519_ecnmul2
+    pts = [g]
+    for e in sc:
+        x, y = pts[-1]
+        xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        f1(e, x, y, xo, yo)
+        assert (xo.raw[:32], yo.raw[:32]) == oracle_ecnmul_edwards("X25519", e, x, y)
+        if xo.raw[:32] != bytes(32):
+            pts.append((xo.raw[:32], yo.raw[:32]))
+    for i in range(len(sc) - 1):
+        (x1, y1), (x2, y2) = pts[i % len(pts)], pts[(i + 3) % len(pts)]
+        xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        f2(sc[i], x1, y1, sc[i + 1], x2, y2, xo, yo)
+        assert (xo.raw[:32], yo.raw[:32]) == oracle_ecnmul2("X25519", sc[i], x1, y1, sc[i + 1], x2, y2)
