@@ -4,7 +4,7 @@
 N=${1:-1}
 OUT=gpurun_out/sweep_n$N.jsonl
 : > $OUT
-for LG in 20 22 24 26 28; do
+for LG in ${SWEEP_LGS:-20 22 24 26 28}; do
   PER=$(( (1 << LG) / N ))
   if [ "$N" = "1" ]; then
     python bench.py --gpus 1 --steps 3 --warmup 3 --keys $PER --no-extra --no-cpu-baseline --parity-keys 65536 >> $OUT
