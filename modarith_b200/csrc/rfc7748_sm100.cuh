@@ -5,7 +5,8 @@
 // frame behind 522 calls).  Here the step keeps 4 persistent elements (x2,z2,x3,z3) plus
 // x1 and 4 temporaries, all in registers, every field call inlined into straight-line
 // IMAD.WIDE chains; the scalar is consumed by shifting it left one bit per step so no
-// register is indexed dynamically; cswap is the mask form (pseudo.py:1006-1013).
+// register is indexed dynamically; the two conditional swaps of the reference's step are
+// replaced by a masked choice of the two operands of its doubling half (see the step).
 #pragma once
 #include "mab_field.cuh"
 
