@@ -38,3 +38,19 @@ void ref_ecnmul2_batch(const char *e, const char *x1, const char *y1, const char
         ecn_nist256_get(&R, xo + o, yo + o);
     }
 }
+
+/* The flow of the reference's testcurve.c main (testcurve.c:213-300) with a selectable iteration count:
+ * P = Q = generator; `iters` times P = a*P; then `iters` times P = a*P + b*Q.  Writes the generator, the
+ * point after the first loop and the final point (affine, big-endian). */
+__attribute__((visibility("default")))
+void ref_testcurve_chain(const char *a, const char *b, int iters, char *gx, char *gy, char *x1, char *y1, char *x2, char *y2) {
+    point P, Q;
+    int i;
+    ecn_nist256_gen(&P);
+    ecn_nist256_get(&P, gx, gy);
+    ecn_nist256_cpy(&P, &Q);
+    for (i = 0; i < iters; i++) ecn_nist256_mul(a, &P);
+    ecn_nist256_get(&P, x1, y1);
+    for (i = 0; i < iters; i++) ecn_nist256_mul2(a, &P, b, &Q, &P);
+    ecn_nist256_get(&P, x2, y2);
+}

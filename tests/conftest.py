@@ -35,6 +35,12 @@ def golden_ecn2():
 
 
 @pytest.fixture(scope="session")
+def golden_testcurve():
+    with open(os.path.join(ROOT, "tests", "golden", "testcurve.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def golden_field():
     with open(os.path.join(ROOT, "tests", "golden", "field.json")) as f:
         return json.load(f)

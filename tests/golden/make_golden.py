@@ -234,7 +234,35 @@ def ecn2_vectors(curve="NIST256"):
     return out
 
 
+def testcurve_chain(curve, iters=150):
+    """The reference's own group test (testcurve.c main): its per-curve constants order, r1, r2 (= order - r1),
+    n1, n2 are read from /root/reference/testcurve.c at generation time; the generator comes from ecnXXXgen;
+    the two timing loops (P = n1*P; then P = n1*P + n2*Q with Q the generator) are run `iters` times each
+    instead of 10000 through the same reference functions (oracle/ref_curve_shim.c)."""
+    import re
+    src = open("/root/reference/testcurve.c").read()
+    blk = src[src.index("#ifdef %s\n    const char order" % curve):]
+    blk = blk[:blk.index("#endif")]
+    consts = {k: re.search(r'const char %s\[\]=\s*"([0-9A-Fa-f]+)"' % k, blk).group(1) for k in ("order", "r1", "r2", "n1", "n2")}
+    lib = ref(curve + "_curve")
+    be = lambda h: int(h, 16).to_bytes(32, "big")
+    bufs = [ctypes.create_string_buffer(32) for _ in range(6)]
+    lib.ref_testcurve_chain(be(consts["n1"]), be(consts["n2"]), ctypes.c_int(iters), *bufs)
+    gx, gy, x1, y1, x2, y2 = (b.raw[:32].hex() for b in bufs)
+    out = dict(consts, iters=iters, gx=gx, gy=gy, x1=x1, y1=y1, x2=x2, y2=y2)
+    # the two pass/fail checks of testcurve.c: order*G = O, r1*G + r2*G = O
+    xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    lib.ref_ecnmul_batch(be(consts["order"]), bytes.fromhex(gx), bytes.fromhex(gy), xo, yo, ctypes.c_size_t(1), 1)
+    out["mul_test"] = [xo.raw[:32].hex(), yo.raw[:32].hex()]
+    lib.ref_ecnmul2_batch(be(consts["r1"]), bytes.fromhex(gx), bytes.fromhex(gy), be(consts["r2"]), bytes.fromhex(gx), bytes.fromhex(gy),
+                          xo, yo, ctypes.c_size_t(1), 1)
+    out["mul2_test"] = [xo.raw[:32].hex(), yo.raw[:32].hex()]
+    return out
+
+
 def main():
+    with open(os.path.join(HERE, "testcurve.json"), "w") as f:
+        json.dump({"NIST256": testcurve_chain("NIST256"), "ED25519": testcurve_chain("ED25519")}, f, indent=1)
     with open(os.path.join(HERE, "ecn.json"), "w") as f:
         json.dump({"NIST256": ecn_vectors("NIST256"), "ED25519": ecn_vectors("ED25519")}, f, indent=1)
     with open(os.path.join(HERE, "ecn2.json"), "w") as f:

@@ -113,3 +113,63 @@ def test_gpu_large_batch_is_position_independent(curve, prime):
     assert np.array_equal(xo, x0[idx]) and np.array_equal(yo, y0[idx])
     xe, ye = _gpu(curve, e[:0], gx[:0], gy[:0], f[:0], gx[:0], gy[:0])
     assert xe.shape == (0, 32)
+
+
+# ---- the reference's own group test, testcurve.c main (generator, order*G = O, r1*G + r2*G = O, the two
+# ---- iterated loops P = n1*P and P = n1*P + n2*G run 150 times each by the reference's own functions) ----
+def _chain(mul, mul2, t):
+    be = lambda h: int(h, 16).to_bytes(32, "big")
+    g = (bytes.fromhex(t["gx"]), bytes.fromhex(t["gy"]))
+    assert mul(be(t["order"]), *g) == (bytes(32), ONE)                                   # "MUL test"
+    assert mul2(be(t["r1"]), *g, be(t["r2"]), *g) == (bytes(32), ONE)                    # "MUL2 test"
+    a, b = be(t["n1"]), be(t["n2"])
+    P = g
+    for _ in range(t["iters"]):
+        P = mul(a, *P)
+    assert (P[0].hex(), P[1].hex()) == (t["x1"], t["y1"])
+    for _ in range(t["iters"]):
+        P = mul2(a, *P, b, *g)
+    assert (P[0].hex(), P[1].hex()) == (t["x2"], t["y2"])
+
+
+@pytest.mark.parametrize("curve,prime", CURVES)
+def test_testcurve_flow_oracle(golden_testcurve, curve, prime):
+    one = oracle_ecnmul if curve == "NIST256" else oracle_ecnmul_edwards
+    _chain(lambda e, x, y: one(prime, e, x, y), lambda e, x1, y1, f, x2, y2: oracle_ecnmul2(prime, e, x1, y1, f, x2, y2),
+           golden_testcurve[curve])
+
+
+@pytest.mark.parametrize("curve,prime", CURVES)
+def test_testcurve_flow_hostsim(hostsim, golden_testcurve, curve, prime):
+    f1, f2 = getattr(hostsim, "sim_%s_ecnmul" % curve), getattr(hostsim, "sim_%s_ecnmul2" % curve)
+
+    def mul(e, x, y):
+        xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        f1(e, x, y, xo, yo)
+        return xo.raw[:32], yo.raw[:32]
+
+    def mul2(e, x1, y1, f, x2, y2):
+        xo, yo = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+        f2(e, x1, y1, f, x2, y2, xo, yo)
+        return xo.raw[:32], yo.raw[:32]
+
+    _chain(mul, mul2, golden_testcurve[curve])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("curve,prime", CURVES)
+def test_testcurve_flow_gpu(golden_testcurve, curve, prime):
+    import torch
+    from modarith_b200.ecn import ecnmul, ecnmul2
+    row = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).reshape(1, 32).cuda()
+    back = lambda t: t.cpu().numpy().tobytes()
+
+    def mul(e, x, y):
+        xo, yo = ecnmul(curve, row(e), row(x), row(y))
+        return back(xo), back(yo)
+
+    def mul2(e, x1, y1, f, x2, y2):
+        xo, yo = ecnmul2(curve, row(e), row(x1), row(y1), row(f), row(x2), row(y2))
+        return back(xo), back(yo)
+
+    _chain(mul, mul2, golden_testcurve[curve])
