@@ -173,3 +173,29 @@ def test_testcurve_flow_gpu(golden_testcurve, curve, prime):
         return back(xo), back(yo)
 
     _chain(mul, mul2, golden_testcurve[curve])
+
+
+def test_argument_checks_need_no_gpu():
+    from modarith_b200 import ecn
+    a = np.zeros((3, 32), dtype=np.uint8)
+    with pytest.raises(ValueError):
+        ecn.ecnmul("SECP256K1", a, a, a)
+    import torch
+    if not torch.cuda.is_available():
+        from modarith_b200.lib import MabError
+        with pytest.raises(MabError):
+            ecn.ecnmul("NIST256", a, a, a)                 # no CPU fallback
+
+
+@pytest.mark.gpu
+def test_gpu_host_arrays_round_trip(golden_ecn2):
+    from modarith_b200 import ecn
+    rows = golden_ecn2["NIST256"][:8]
+    cols = [np.frombuffer(b"".join(bytes.fromhex(r[k]) for r in rows), dtype=np.uint8).reshape(-1, 32).copy() for k in KEYS]
+    xo, yo = ecn.ecnmul2("NIST256", *cols)
+    assert isinstance(xo, np.ndarray)
+    assert [xo[i].tobytes().hex() for i in range(8)] == [r["xo"] for r in rows]
+    with pytest.raises(ValueError):
+        ecn.ecnmul2("NIST256", cols[0][:, :31], *cols[1:])
+    with pytest.raises(ValueError):
+        ecn.ecnmul("NIST256", cols[0], cols[1][:4], cols[2])
