@@ -13,7 +13,7 @@ FUNCS = {
     "nop": "for (int i = 0; i < L; i++) r[i] = a[i] ^ b[i];",
     "mul": "F::mul(r, a, b);", "sqr": "F::sqr(r, a); (void)b;", "add": "F::add(r, a, b);",
     "sub": "F::sub(r, a, b);", "mli": "F::mli(r, a, b[0]);", "mla": "F::mla(r, a, 121665u, b);",
-    "neg": "F::neg(r, a); (void)b;",
+    "neg": "F::neg(r, a); (void)b;", "add_tt": "F::add_tt(r, a, b);", "sub_tt": "F::sub_tt(r, a, b);",
 }
 
 def mix(name):
