@@ -317,6 +317,22 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
             del ua, ub, uc
         out[name] = res
         del x, y, r, xs, ys, rs
+    # the generator's fall-back plan (any odd modulus: full Montgomery with real multiplies), SURVEY.md 8f row 2
+    for name in ("SECP256K1", "NIST256ORDER"):
+        try:
+            F = Field(name, dev)
+            m, iters = 1 << 20, 256
+            x, _ = F.modimp(torch.randint(0, 256, (m, F.Nbytes), dtype=torch.uint8, device=dev, generator=gen))
+            y, _ = F.modimp(torch.randint(0, 256, (m, F.Nbytes), dtype=torch.uint8, device=dev, generator=gen))
+            r = F.alloc(m)
+            L = F.Nlimbs
+            t = _time(lambda: F.bench_modmul(x, y, r, iters), 2)
+            out[name] = {"modmul_register_resident": {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
+                                                      "imad_frac": (m * iters / t * L * L / pk) if pk else None,
+                                                      "note": "MontgomeryFull plan: 2.5 L^2 wide multiplies per modmul"}}
+            del x, y, r
+        except Exception as ex:
+            out[name] = {"error": str(ex)[:200]}
     return out
 
 
