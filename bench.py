@@ -97,12 +97,13 @@ def cpu_baseline(sample_keys):
     if lib is None:
         return cpu_baseline_port(sample_keys)
     cores = os.cpu_count() or 1
-    k, u = make_inputs(min(4096, sample_keys), 1)
-    dt, _ = time_reference(lib, k, u, cores)              # warm-up + rate estimate
+    k, u = make_inputs(4096 if sample_keys <= 0 else min(4096, sample_keys), 1)
+    time_reference(lib, k, u, cores)                      # warm-up: thread pool, page faults
+    dt, _ = time_reference(lib, k, u, cores)              # rate estimate
     rate = k.shape[0] / dt
     n = sample_keys if sample_keys > 0 else 0
     if n == 0:
-        n = int(max(8192, min(1 << 20, rate * 1.5)))      # ~1.5 s wall on all cores (about 25-50 CPU-seconds)
+        n = int(max(1 << 17, min(1 << 20, rate * 1.5)))   # ~1.5 s wall on all cores (about 25-50 CPU-seconds)
     k, u = make_inputs(n, 7748)
     dt, _ = time_reference(lib, k, u, cores)
     return {"value": n / dt, "unit": "scalar-mults/s", "cores": cores, "kind": "reference",
