@@ -792,17 +792,46 @@ class MontgomeryFull(Montgomery):
     def reduce_small(self, asm, T):
         raise NotImplementedError
 
+    # MAB_MONTY=separate keeps the first formulation (product, then Q = T_lo*n', U = Q*p: 2.5 L^2 wide multiplies)
+    interleaved = os.environ.get("MAB_MONTY", "interleaved") != "separate"
+
+    def _mont(self, asm, a, b):
+        """a*b*R^-1 mod p, fully reduced."""
+        if not self.interleaved:
+            return self._redc(asm, satmul.product(asm, a, b))
+        L = self.L
+        n0 = self.nprime & M32
+        return self._cond_sub_p9(asm, satmul.montgomery_interleaved(asm, a, b, words(self.p, L), n0))
+
+    def build_mul(self):
+        asm = Asm(self.name + ".mul")
+        a, b = self._io(asm, ["a", "b"])
+        self._outs(asm, self._mont(asm, a, b))
+        return asm
+
+    def build_sqr(self):
+        if not self.interleaved:
+            return super().build_sqr()
+        asm = Asm(self.name + ".sqr")
+        (a,) = self._io(asm, ["a"])
+        self._outs(asm, self._mont(asm, a, a))
+        return asm
+
     def _small_times(self, asm, a, bname, c=None):
         """a*b (+c) for a small plain integer b: b is lifted into Montgomery form with one
         multiplication by R^2 (b*R), then multiplied in; no R factor remains (monty.py:876-978
         gets there with a Barrett-Dhem estimate instead)."""
         L = self.L
         r2 = words(self.R2, L)
-        t = satmul.times_small(asm, r2, bname)                       # R^2 * b  (L+1 words)
-        # Montgomery-reduce R^2*b (< 2^32 * p): pad to 2L words
-        bm = self._redc(asm, t + [0] * (2 * L - (L + 1)))            # = b*R mod p
-        T = satmul.product(asm, a, bm)
-        r = self._redc(asm, T)
+        if self.interleaved:
+            bm = self._mont(asm, r2, [bname] + [0] * (L - 1))        # (R^2 mod p) * b * R^-1 = b*R mod p; zero rows skipped
+            r = self._mont(asm, a, bm)
+        else:
+            t = satmul.times_small(asm, r2, bname)                       # R^2 * b  (L+1 words)
+            # Montgomery-reduce R^2*b (< 2^32 * p): pad to 2L words
+            bm = self._redc(asm, t + [0] * (2 * L - (L + 1)))            # = b*R mod p
+            T = satmul.product(asm, a, bm)
+            r = self._redc(asm, T)
         if c is None:
             return r
         s = asm.tmp(L + 1)

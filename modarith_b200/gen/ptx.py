@@ -121,17 +121,18 @@ class Asm:
         return self._emit("prmt", d, (a, b, sel))
 
     # ---- carry-chain helpers -------------------------------------------
-    def wide_chain(self, slots, last_carry_to=None, first=True):
+    def wide_chain(self, slots, last_carry_to=None, first=True, carry_in=False):
         """One carry chain of 32x32->64 multiply-accumulates.
 
         slots: list of (lo_dst, hi_dst, a, b, lo_addend, hi_addend); consecutive
         slots are adjacent 64-bit windows so the carry ripples upward.
         last_carry_to: (dst, addend) receiving the final carry, or None if the
         carry out of the last slot is provably zero (checked by the interpreter).
+        carry_in: the first slot consumes the carry flag left by the preceding instruction.
         """
         n = len(slots)
         for k, (lo, hi, a, b, clo, chi) in enumerate(slots):
-            self.madlo(lo, a, b, clo, cin=(k > 0), cout=True)
+            self.madlo(lo, a, b, clo, cin=(k > 0 or carry_in), cout=True)
             last = (k == n - 1) and last_carry_to is None
             self.madhi(hi, a, b, chi, cin=True, cout=not last)
         if last_carry_to is not None:

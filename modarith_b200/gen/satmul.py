@@ -58,11 +58,13 @@ class _Acc:
         return self.reg[k]
 
 
-def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
-    """prods: list of (s, a, b) with s ascending in steps of 2; window (s, s+1)."""
+def _row_chain(asm: Asm, acc: _Acc, prods, nwords, carry_in=False):
+    """prods: list of (s, a, b) with s ascending in steps of 2; window (s, s+1).  carry_in: the first
+    window also takes the carry flag left by the instruction emitted just before."""
     if not prods:
+        assert not carry_in
         return
-    fresh = all(not acc.live[s] and not acc.live[s + 1] for s, _, _ in prods)
+    fresh = (not carry_in) and all(not acc.live[s] and not acc.live[s + 1] for s, _, _ in prods)
     if fresh:
         # untouched windows: independent wide multiplies, no carries can arise
         for s, a, b in prods:
@@ -72,7 +74,7 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
             acc.ub[s + 1] = M32 - 1
         return
     slots = []
-    cin = 0
+    cin = 1 if carry_in else 0
     for s, a, b in prods:
         clo, chi = acc.src(s), acc.src(s + 1)
         slots.append((acc.dst(s), acc.dst(s + 1), a, b, clo, chi))
@@ -83,10 +85,10 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords):
     top = prods[-1][0] + 2
     if top < nwords and (cin or not SMART_CAPTURE):
         c = acc.src(top)
-        asm.wide_chain(slots, last_carry_to=(acc.dst(top), c))
+        asm.wide_chain(slots, last_carry_to=(acc.dst(top), c), carry_in=carry_in)
         acc.ub[top] = min(M32, acc.ub[top] + 1)
     else:
-        asm.wide_chain(slots, last_carry_to=None)
+        asm.wide_chain(slots, last_carry_to=None, carry_in=carry_in)
 
 
 def _merge(asm: Asm, E: _Acc, O: _Acc, nwords, link=False):
@@ -253,4 +255,57 @@ def product_low(asm: Asm, a, b):
         asm.madlo(d, x, y, top)
         top = d
     T[L - 1] = top
+    return T
+
+
+def montgomery_interleaved(asm: Asm, a, b, pw, n0):
+    """a*b*2^(-32L) mod p before the final conditional subtraction, as L+1 words (< 2p for a, b < p).
+
+    Word-serial Montgomery multiplication on the same even/odd accumulators as `product_eo`
+    (monty.py:663-872 interleaves one reduction step per column; the pairing of the two arrays follows
+    the even/odd scheme known from GPU big-number libraries): round i adds the row a*b[i] at windows
+    i, i+1, ..., then m = T[i]*n0 mod 2^32 and the row m*p at the same windows, which zeroes word i.
+    The 64-bit window (i, i+1) belongs to array X (E for even i, O for odd i); the other array Y holds
+    word i as the HIGH word of its window (i-1, i), final by now.  Y[i] is added into X[i] with one add
+    whose carry-out has exactly the weight of Y's next window (i+1, i+2) -- it becomes the carry-in of
+    the m*p chain on Y.  The carry out of word i when m*p[0] zeroes it stays inside X's window.
+    2L^2 wide multiplies + L plain multiplies; b[i] may be the literal 0 (row skipped), a and pw may be
+    literals."""
+    L = len(a)
+    assert len(b) == L and len(pw) == L
+    n = 2 * L + 2
+    E, O = _Acc(asm, n), _Acc(asm, n)
+    for i in range(L):
+        X, Y = (E, O) if i % 2 == 0 else (O, E)
+        if not (isinstance(b[i], int) and b[i] == 0):
+            _row_chain(asm, X, [(i + j, a[j], b[i]) for j in range(0, L, 2)], n)
+            _row_chain(asm, Y, [(i + j, a[j], b[i]) for j in range(1, L, 2)], n)
+        # fold the finished word i of Y into X's window; its carry belongs to word i+1 = Y's next window
+        carry = False
+        if Y.live[i]:
+            d = asm.tmp()
+            asm.add(d, X.src(i), Y.reg[i], cout=True)
+            X.reg[i], X.live[i], X.ub[i] = d, True, M32
+            carry = True
+        if not X.live[i]:                      # nothing has reached word i yet (leading zero rows): m = 0
+            assert not carry
+            continue
+        m = asm.tmp()
+        asm.nocheck.add(len(asm.ins))
+        asm.mullo(m, X.reg[i], n0)
+        # pw[j] == 0 still occupies its window (the chain has to pass the carry on)
+        _row_chain(asm, Y, [(i + j, pw[j], m) for j in range(1, L, 2)], n, carry_in=carry)
+        _row_chain(asm, X, [(i + j, pw[j], m) for j in range(0, L, 2)], n)
+    # words below L are zero (or dead); the result is E + O over words L .. 2L
+    T = []
+    started = False
+    for k in range(L, 2 * L + 1):
+        e, o = E.src(k), O.src(k)
+        if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
+            T.append(o if (isinstance(e, int) and e == 0) else e)
+            continue
+        d = asm.tmp()
+        asm.add(d, e, o, cin=started, cout=(k < 2 * L))
+        started = True
+        T.append(d)
     return T
