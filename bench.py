@@ -330,7 +330,7 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
             t = _time(lambda: F.bench_modmul(x, y, r, iters), 2)
             out[name] = {"modmul_register_resident": {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
                                                       "imad_frac": (m * iters / t * L * L / pk) if pk else None,
-                                                      "note": "MontgomeryFull plan: 2.5 L^2 wide multiplies per modmul"}}
+                                                      "note": "MontgomeryFull plan: word-serial Montgomery, 2 L^2 wide multiplies + L plain ones per modmul"}}
             del x, y, r
         except Exception as ex:
             out[name] = {"error": str(ex)[:200]}
