@@ -759,15 +759,18 @@ class Montgomery(Plan):
 class MontgomeryFull(Montgomery):
     """Montgomery form, R = 2^(32L), for ANY odd modulus below 2^(32L) -- the fallback that makes
     the generator total, as monty.py is for the reference (full Montgomery, ndash != 1:
-    monty.py:740-751,2237-2244; e.g. group orders, monty.py:2110-2127).  Separated-operand REDC:
+    monty.py:740-751,2237-2244; e.g. group orders, monty.py:2110-2127).
+
+    Default: word-serial Montgomery multiplication interleaved with the product on the even/odd
+    accumulators (satmul.montgomery_interleaved): 2 L^2 wide multiplies + L plain ones per modmul,
+    squaring by the same routine, small multiples via the lift b -> b*R (one short and one full
+    multiplication).  MAB_MONTY=separate selects the first formulation, kept for comparison:
 
         Q = T_lo * (-p^-1 mod R)  mod R      L(L+1)/2 wide multiplies by a constant
         U = Q * p                            L^2 wide multiplies by a constant
         a*b*R^-1 = (T + U) / R               one 2L-word add chain, one conditional subtraction
 
-    2.5 L^2 wide multiplies per modmul instead of L^2: correct first; interleaving the reduction
-    rows with the product rows (2 L^2 + L) is the known next step.  Stored values are fully
-    reduced, in [0, p)."""
+    Stored values are fully reduced, in [0, p)."""
 
     def __init__(self, prime):
         Plan.__init__(self, prime)
