@@ -72,3 +72,29 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dp, fn)).read()
                 assert "field_oracle" not in text and "oracle/" not in text.replace("oracle/_ref", "").replace(
                     "oracle/build_ref", "").replace("oracle/addchain", ""), os.path.join(dp, fn)
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/modarith_b200.h compiled as C11 by gcc, linked against the shared library, run without a GPU:
+    the boundary is a C ABI (no C++ or torch types), and a call that needs no device works."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "consumer.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "modarith_b200.h"\n'
+        "int main(void) {\n"
+        "  int (*ladder)(const char *, const char *, char *, size_t, void *) = mab_X25519_rfc7748;\n"
+        "  int (*host)(const char *, const char *, char *, size_t, int) = mab_X448_rfc7748_host;\n"
+        "  int (*mul2)(const char *, const char *, const char *, const char *, const char *, const char *, char *, char *, size_t, void *) = mab_NIST256_ecnmul2;\n"
+        "  if (!ladder || !host || !mul2) return 2;\n"
+        '  printf("%s|%s\\n", mab_version(), mab_error_string(0));\n'
+        "  return ladder(0, 0, 0, 0, 0);                 /* n = 0: nothing to do, no device needed */\n"
+        "}\n")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(built)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", libdir, "-lmodarith_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("modarith_b200") and out.stdout.strip().endswith("|ok")
