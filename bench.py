@@ -45,8 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="keys in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the X448 / P-256 side measurements")
-    ap.add_argument("--parity-keys", type=int, default=2048,
-                    help="keys of rank 0's first step checked against the reference build before timing")
+    ap.add_argument("--parity-keys", type=int, default=-1,
+                    help="keys of EVERY rank's first step checked against the reference build before timing "
+                         "(-1 = all local keys, capped at 2^20 per rank)")
     return ap.parse_args()
 
 
@@ -433,15 +434,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- parity spot-check against the reference build before timing (rank 0) ------------------
-    ref = load_reference() if rank == 0 else None
+    # ---- parity against the reference build before timing: EVERY rank checks its own shard ------
+    # (all local keys by default: 2^20 per rank is ~2 s of the reference's C on the host cores, which the
+    # ranks share -- each takes cores/world threads)
+    ref = load_reference()
     parity = None
+    parity_n = 0
+    want0 = None
     out0 = rfc7748(CURVE, dk[0], du[0], dv[0])
     torch.cuda.synchronize()
     if ref is not None:
-        m = min(args.parity_keys, n_local)
-        _, want = time_reference(ref, hk[0][:m].numpy(), hu[0][:m].numpy(), os.cpu_count() or 1)
-        parity = bool(np.array_equal(out0[:m].cpu().numpy(), want))
+        m = min(n_local, 1 << 20) if args.parity_keys < 0 else min(args.parity_keys, n_local)
+        threads = max(1, (os.cpu_count() or 1) // world)
+        _, want0 = time_reference(ref, hk[0][:m].numpy(), hu[0][:m].numpy(), threads)
+        parity = bool(np.array_equal(out0[:m].cpu().numpy(), want0))
+        parity_n = m
 
     # ---- device-resident throughput --------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -485,9 +492,11 @@ def main():
     os.environ.pop("MAB_HOST_ZEROCOPY")
     e2e_s, e2e_steps = run_e2e(args.steps)
     e2e_launches = args.steps
-    if ref is not None and parity:
-        _, want = time_reference(ref, hk[(args.steps - 1) % NSETS][:1024].numpy(), hu[(args.steps - 1) % NSETS][:1024].numpy(), 0)
-        parity = bool(np.array_equal(hv[:1024].numpy(), want))
+    if want0 is not None:
+        # the host-buffer route on the same keys (one more call, outside the timed region)
+        hv.zero_()
+        rfc7748(CURVE, hk[0], hu[0], hv, device=local)
+        parity = parity and bool(np.array_equal(hv[:parity_n].numpy(), want0))
 
     # ---- optional result gather over NVLink, timed apart ----------------------------------------------
     gather_ms = None
@@ -504,9 +513,16 @@ def main():
 
     # ---- max over ranks --------------------------------------------------------------------------------
     tt = torch.tensor([ms, e2e_s * 1e3, gather_ms or 0.0], dtype=torch.float64, device=dev)
+    # parity: AND over ranks (min), keys compared summed over ranks; -1 = no reference build on this rank
+    pp = torch.tensor([(-1 if parity is None else int(parity)), parity_n], dtype=torch.int64, device=dev)
+    pmin, psum = pp.clone(), pp.clone()
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(psum, op=dist.ReduceOp.SUM)
     ms, e2e_ms, gather_ms_max = (float(x) for x in tt.cpu())
+    parity = None if int(pmin[0]) < 0 else bool(int(pmin[0]))
+    parity_total = int(psum[1])
 
     if rank == 0:
         value = n_total * args.steps / (ms * 1e-3)
@@ -563,7 +579,9 @@ def main():
                     "staged_pipeline_value_rank0": staged_rate},
             "gpu_launches": launches, "gpu_launches_e2e": e2e_launches,
             "roofline": roof, "cpu_baseline": base, "clocks": clocks, "parity_spot_check": parity,
-            "parity_keys": min(args.parity_keys, n_local),
+            "parity_keys": parity_total, "parity_ranks": world,
+            "parity_note": "every rank compared its own keys (device-pointer call and host-buffer call) byte-for-byte "
+                           "with the reference's generated C; parity_spot_check = AND over ranks, parity_keys = sum",
             "gather_ms": gather_ms_max if world > 1 else None, "gpu": props.name, "sms": props.multi_processor_count,
             "extra": extra,
         }

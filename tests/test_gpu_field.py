@@ -243,6 +243,97 @@ def test_p256_full_size_properties():
     assert int(F.modcmp(r, s).sum()) == n
 
 
+def test_p256_full_size_sample_vs_reference_build(ref_libs):
+    """BASELINE config 4 at its stated size (2^24 P-256 elements through modimp -> op -> modexp) with a 2^20
+    sub-sample -- one contiguous block of 2^19 elements plus every 32nd element of the batch -- compared
+    byte-for-byte with the reference's generated C (monty.py 64 NIST256) for modmul, modsqr, modinv, modsqrt,
+    modadd and modsub, modimp status included.  Corner rows of SURVEY.md 8d-4 are planted inside the sample:
+    p-1, p, p+1, 2^256-1, 0, 1."""
+    if "NIST256" not in ref_libs:
+        pytest.skip("oracle/_ref not built")
+    F = _field("NIST256")
+    p = PRIMES["NIST256"].p
+    n = 1 << 24
+    gen = torch.Generator(device="cuda").manual_seed(2561)
+    a8 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=gen)
+    b8 = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=gen)
+    base = 5 * (1 << 20) + 17                             # contiguous block, not block-aligned
+    idx = torch.cat([torch.arange(base, base + (1 << 19), device="cuda"), torch.arange(0, n, 32, device="cuda")])
+    assert idx.numel() == 1 << 20
+    for j, v in enumerate([p - 1, p, p + 1, (1 << 256) - 1, 0, 1]):
+        a8[base + j] = torch.from_numpy(np.frombuffer(v.to_bytes(32, "big"), dtype=np.uint8).copy()).cuda()
+    x, st = F.modimp(a8)
+    y, _ = F.modimp(b8)
+    a, b = a8[idx].cpu().numpy(), b8[idx].cpu().numpy()
+    del a8, b8
+    r = F.alloc(n)
+    out = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    for op in ("mul", "sqr", "inv", "sqrt", "add", "sub"):
+        if op == "mul": F.modmul(x, y, r)
+        if op == "sqr": F.modsqr(x, r)
+        if op == "inv": F.modinv(x, None, r)
+        if op == "sqrt": F.modsqrt(x, None, r)
+        if op == "add": F.modadd(x, y, r)
+        if op == "sub": F.modsub(x, y, r)
+        F.modexp(r, out)
+        want, wst = util.ref_field_batch(ref_libs["NIST256"], op, a, b if op in ("mul", "add", "sub") else None)
+        got = out[idx].cpu().numpy()
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        assert bad.size == 0, (op, "first mismatching sample rows", bad[:8].tolist())
+        assert np.array_equal(st[idx].cpu().numpy(), wst)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_modfsb_on_noncanonical_stored_values(name):
+    """modfsb (pseudo.py:272-283) returns 0 and reduces when the stored value is >= p.  Stored values >= p
+    exist for the weakly reduced plans (2^255-19: anything below 2^256; 2^448-2^224-1: below 2^448) and are
+    planted here as raw limb planes; the fully reduced Montgomery plans only ever hold values below p, so
+    for them the flag is 1 and the value unchanged -- both asserted."""
+    from modarith_b200.gen.plan import make_plan
+    F = _field(name)
+    P = PRIMES[name]
+    plan = make_plan(P)
+    p, L = P.p, F.Nlimbs
+    rng = random.Random(5)
+    top = plan.bound
+    vals = [0, 1, p - 1] + [rng.randrange(p) for _ in range(40)]
+    if top > p:
+        vals += [p, p + 1, top - 1, (p + top) // 2] + [rng.randrange(p, top) for _ in range(40)]
+    planes = np.zeros((L, len(vals)), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        for j in range(L):
+            planes[j, i] = (v >> (32 * j)) & 0xFFFFFFFF
+    x = torch.from_numpy(planes.view(np.int32)).cuda()
+    flags = F.modfsb(x).cpu().tolist()
+    assert flags == [int(v < p) for v in vals]
+    got = x.cpu().numpy().view(np.uint32).astype(object)
+    back = [sum(int(got[j, i]) << (32 * j) for j in range(L)) for i in range(len(vals))]
+    assert back == [v % p for v in vals]
+    if top > p:
+        assert 0 in flags
+
+
+@pytest.mark.parametrize("name", ["NIST256", "SECP256K1", "NIST256ORDER"])
+def test_modshr_montgomery_moduli(name):
+    """modshr on the Montgomery moduli, used the way the reference uses it (modexp / modhaf / rfc7748.c:250:
+    on a canonical plain value): redc first, shift the plain words, compare value and shifted-out bits."""
+    F = _field(name)
+    O = FieldOracle(name)
+    p = O.p
+    rng = random.Random(6)
+    xs = [0, 1, p - 1, p - 2, 255, 256] + [rng.randrange(p) for _ in range(300)]
+    x = F.from_ints(xs)
+    plain = F.alloc(len(xs))
+    for sh in (1, 8, 31):
+        F.redc(x, plain)
+        out = F.modshr(sh, plain).cpu().tolist()
+        pw = plain.cpu().numpy().view(np.uint32).astype(object)
+        got = [sum(int(pw[j, i]) << (32 * j) for j in range(F.Nlimbs)) for i in range(len(xs))]
+        assert got == [v >> sh for v in xs]
+        assert out == [v & ((1 << sh) - 1) for v in xs]
+        assert [(g, o) for g, o in zip(got, out)] == [O.modshr(sh, v) for v in xs]
+
+
 def test_unsaturated_comparison_kernel():
     """csrc/mab_unsat29.cuh (the reference's radix-2^29 x 9 plan, kept only to be measured against the
     saturated plan) computes a * b^k mod 2^255-19."""

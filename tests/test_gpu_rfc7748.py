@@ -133,6 +133,30 @@ def test_random_vs_reference_build(ref_libs, curve, n):
 
 
 @pytest.mark.parametrize("curve", CURVES)
+def test_full_size_every_key_vs_reference_build(ref_libs, curve):
+    """BASELINE configs 2 and 3 at their stated size: 2^20 raw PCG64(7748) key/point pairs, EVERY output
+    compared byte-for-byte with rfc7748() of the reference's own generated C (rfc7748.c:156-256 with
+    pseudo.py 64 X25519 / monty.py 64 X448 pasted in; OpenMP over the host cores).  Fixed rows of SURVEY.md
+    8d-2 are planted at the front: u in {0, 1, p-1, p, p+1, 2^Nbits-1, generator}, k in {0, all-ones}."""
+    if curve not in ref_libs:
+        pytest.skip("oracle/_ref not built")
+    P = PRIMES[curve]
+    nb = P.nbytes
+    n = 1 << 20
+    k, u = util.random_bytes(7748, n, nb), util.random_bytes(7749, n, nb)
+    row = 0
+    for uv in (0, 1, P.p - 1, P.p, P.p + 1, (1 << P.nbits) - 1, P.generator):
+        for kv in (0, (1 << (8 * nb)) - 1):
+            u[row] = np.frombuffer((uv % (1 << (8 * nb))).to_bytes(nb, "little"), dtype=np.uint8)
+            k[row] = np.frombuffer(kv.to_bytes(nb, "little"), dtype=np.uint8)
+            row += 1
+    out = _gpu(curve, k, u)
+    want = util.ref_rfc7748_batch(ref_libs[curve], k, u)
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, (curve, "first mismatching keys", bad[:8].tolist())
+
+
+@pytest.mark.parametrize("curve", CURVES)
 def test_empty_and_tiny_batches(curve):
     nb = PRIMES[curve].nbytes
     e = np.zeros((0, nb), dtype=np.uint8)
