@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="keys in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the X448 / P-256 side measurements")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from ONE process: device-resident launches on every device, and the end-to-end "
+                         "figure through mab_X25519_rfc7748_host_multi (one host thread per GPU inside the library)")
     ap.add_argument("--parity-keys", type=int, default=-1,
                     help="keys of EVERY rank's first step checked against the reference build before timing "
                          "(-1 = all local keys, capped at 2^20 per rank)")
@@ -376,6 +379,101 @@ def run_reference(args, rank):
     return 0
 
 
+def run_single_process(args):
+    """--gpus N --single-process: the C consumer's view of a multi-GPU box.  One process,
+    no torchrun, no NCCL: `value` launches the device-pointer call on every device from this thread (the calls are
+    asynchronous) and takes the slowest device's CUDA-event time; `e2e` is one mab_X25519_rfc7748_host_multi call
+    per step on pinned host buffers holding all N x keys keys."""
+    import numpy as np
+    import torch
+    from modarith_b200 import lib as mlib
+    from modarith_b200.rfc7748 import rfc7748
+    lib = mlib.load()
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit("--single-process --gpus %d needs %d visible devices" % (N, N))
+    n_local, n_total = args.keys, args.keys * N
+    NSETS = 3
+    hk, hu = [], []
+    for s in range(NSETS):
+        ks, us = [], []
+        for g in range(N):
+            k, u = make_inputs(n_local, 7748 + 1000 * s + g)
+            ks.append(k); us.append(u)
+        hk.append(torch.from_numpy(np.concatenate(ks)).pin_memory())
+        hu.append(torch.from_numpy(np.concatenate(us)).pin_memory())
+    hv = torch.empty((n_total, NB), dtype=torch.uint8).pin_memory()
+    dk = [[hk[s][g * n_local:(g + 1) * n_local].to("cuda:%d" % g) for g in range(N)] for s in range(NSETS)]
+    du = [[hu[s][g * n_local:(g + 1) * n_local].to("cuda:%d" % g) for g in range(N)] for s in range(NSETS)]
+    dv = [torch.empty_like(dk[0][g]) for g in range(N)]
+
+    def step(s):
+        for g in range(N):
+            with torch.cuda.device(g):
+                rfc7748(CURVE, dk[s % NSETS][g], du[s % NSETS][g], dv[g])
+
+    def sync():
+        for g in range(N):
+            torch.cuda.synchronize(g)
+
+    for w in range(args.warmup):
+        step(w)
+    sync()
+    ev = []
+    for g in range(N):
+        with torch.cuda.device(g):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ev.append((e0, e1))
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(s)
+    for g in range(N):
+        with torch.cuda.device(g):
+            ev[g][1].record()
+    sync()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1) for e0, e1 in ev)
+    # parity of every device's shard against the reference build (set of the last step)
+    ref = load_reference()
+    parity, pn = None, 0
+    if ref is not None:
+        s = (args.steps - 1) % NSETS
+        m = min(n_local, 1 << 18)
+        parity = True
+        for g in range(N):
+            _, want = time_reference(ref, hk[s][g * n_local:g * n_local + m].numpy(), hu[s][g * n_local:g * n_local + m].numpy(), 0)
+            parity = parity and bool(np.array_equal(dv[g][:m].cpu().numpy(), want))
+            pn += m
+    # end to end through the multi-device C entry point
+    fn = lib.mab_X25519_rfc7748_host_multi
+    for w in range(2):
+        mlib.check(fn(hk[w].data_ptr(), hu[w].data_ptr(), hv.data_ptr(), n_total, N))
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        mlib.check(fn(hk[s % NSETS].data_ptr(), hu[s % NSETS].data_ptr(), hv.data_ptr(), n_total, N))
+    e2e_s = time.perf_counter() - t0
+    if ref is not None:
+        s = (args.steps - 1) % NSETS
+        m = min(n_local, 1 << 18)
+        for g in range(N):
+            _, want = time_reference(ref, hk[s][g * n_local:g * n_local + m].numpy(), hu[s][g * n_local:g * n_local + m].numpy(), 0)
+            parity = parity and bool(np.array_equal(hv[g * n_local:g * n_local + m].numpy(), want))
+    print(json.dumps({
+        "metric": "X25519 scalar-mults/s", "value": n_total * args.steps / (ms * 1e-3), "unit": "scalar-mults/s",
+        "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (saturated radix 2^32)", "data": "synthetic",
+        "mode": "single-process",
+        "config": {"workload": "batched X25519 (rfc7748) %d random scalars/points per GPU" % n_local, "keys_per_gpu": n_local,
+                   "keys_total": n_total, "sharding": "contiguous key ranges, one host thread per device inside the library"},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "e2e": {"value": n_total * args.steps / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": 2 * NB * n_total,
+                "d2h_bytes_per_step": NB * n_total, "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "mab_X25519_rfc7748_host_multi(bk, bu, bv, n, %d) on pinned host buffers" % N},
+        "gpu_launches": args.steps * N, "parity_spot_check": parity, "parity_keys": pn}))
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +481,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.single_process and world == 1 and args.gpus > 1:
+        return run_single_process(args)
 
     import numpy as np
     import torch
@@ -418,7 +518,7 @@ def main():
 
     # inputs: this rank's contiguous range of the global PCG64(7748) batch; three buffer sets are
     # rotated so no step finds its inputs in L2 (3 x 96 MB > 126 MB)
-    NSETS = 3
+    NSETS = 3 if n_local * 3 * NB <= (1 << 30) else 1     # one set is already many times L2 beyond 2^23 keys
     hk, hu = [], []
     for s in range(NSETS):
         k, u = make_inputs(n_local, 7748 + 1000 * s + rank)
@@ -568,7 +668,8 @@ def main():
             "config": {"workload": "batched X25519 (rfc7748) 2^20 random scalars/points per GPU" if n_local == 1 << 20
                        else "batched X25519 (rfc7748) %d random scalars/points per GPU" % n_local,
                        "keys_per_gpu": n_local, "keys_total": n_total, "sharding": "contiguous key ranges, no collective",
-                       "l2": "inputs rotate over 3 buffer sets (288 MB > 126 MB L2); kernel moves 96 B/key",
+                       "l2": ("inputs rotate over 3 buffer sets (288 MB > 126 MB L2); kernel moves 96 B/key" if NSETS == 3 else
+                              "one buffer set of %d MB (>> 126 MB L2); kernel moves 96 B/key" % (n_local * 3 * NB >> 20)),
                        "inputs": "numpy PCG64(7748+...) raw bytes, unclamped / unreduced"},
             "e2e": {"value": e2e, "unit": "scalar-mults/s", "h2d_bytes_per_step": 2 * NB * n_local,
                     "d2h_bytes_per_step": NB * n_local, "ms_per_step": e2e_ms / args.steps,

@@ -143,10 +143,12 @@ MAB_API int mab_probe_unsat29_modmul(const uint32_t *a, const uint32_t *b, uint3
 MAB_DECLARE_FIELD(X25519)
 MAB_DECLARE_FIELD(X448)
 MAB_DECLARE_FIELD(NIST256)
-/* Two moduli outside the three hot-path ones, built with the generator's fall-back plan (full Montgomery,
- * any odd modulus -- monty.py's unshaped case, monty.py:2237-2244): the secp256k1 field prime
- * (monty.py:2066-2067) and the order of the P-256 group (the reference's "00<decimal>" mode, monty.py:2110-2127).
- * Further moduli: python -m modarith_b200.build --prime NAME=<expression>  (INTEGRATION.md). */
+/* Two moduli outside the three hot-path ones: the secp256k1 field prime 2^256 - 2^32 - 977 (monty.py:2066-2067;
+ * here a plain-residue plan that folds 2^256 == 2^32 + 977) and the order of the P-256 group (the reference's
+ * "00<decimal>" mode, monty.py:2110-2127; the generator's fall-back plan: full Montgomery, any odd modulus,
+ * monty.py:2237-2244).  Further moduli: print the header with
+ *   python -m modarith_b200.gen.monty_sm100 "<expression>" -o field_NAME.cuh
+ * and compile it behind this ABI with the three-line unit shown in INTEGRATION.md ("Textual inclusion and further moduli"). */
 MAB_DECLARE_FIELD(SECP256K1)
 MAB_DECLARE_FIELD(NIST256ORDER)
 
@@ -187,6 +189,14 @@ MAB_API int mab_X448_rfc7748_validate(const char *bk, const char *bu, char *bv, 
  * speed, pageable memory works but serialises the copies. */
 MAB_API int mab_X25519_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
 MAB_API int mab_X448_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);
+/* The whole box: what replaces a consumer's loop over keys (the timing loop of the reference's driver,
+ * rfc7748.c:301-304, calls rfc7748() once per key) when more than one GPU is present.  Device g of `ndev`
+ * takes the contiguous key range [g*n/ndev, (g+1)*n/ndev); one host thread and one set of streams per
+ * device, no exchange between devices.  ndev <= 0 uses every visible device; ndev larger
+ * than the device count is MAB_ERR_BADARG.  Page-locked buffers (cudaHostAlloc / cudaHostRegister) are read
+ * and written in place by every GPU; pageable buffers are staged per device.  Returns when bv is complete. */
+MAB_API int mab_X25519_rfc7748_host_multi(const char *bk, const char *bu, char *bv, size_t n, int ndev);
+MAB_API int mab_X448_rfc7748_host_multi(const char *bk, const char *bu, char *bv, size_t n, int ndev);
 
 #ifdef __cplusplus
 }

@@ -171,8 +171,18 @@ template <class F> struct Field {
     uint32_t t[L];
 #pragma unroll
     for (int i = 0; i < L; i++) t[i] = (r < 8u * F::NBYTES && (r >> 5) == (unsigned)i) ? (1u << (r & 31)) : 0u;
-    (void)F::canon(t, t);
-    F::nres(a, t);
+    import_raw(a, t);
+  }
+  // raw words (any value below 2^(32L)) -> stored form; returns 1 iff the value was < p.  Plain-residue plans
+  // canonicalise (their canon covers the whole raw range by construction).  Montgomery plans multiply the RAW
+  // words by R^2: (w*R2 + m*p)/R < 2p for any w < R, so the product's own final subtraction is enough whatever
+  // the ratio 2^(32L)/p is -- moduli with spare bits in their top word included (canon alone, one conditional
+  // subtraction, would be short there); canon still supplies the w < p flag.
+  static MAB_DEV uint32_t import_raw(uint32_t (&a)[L], const uint32_t (&w)[L]) {
+    uint32_t t[L];
+    const uint32_t lt = F::canon(t, w);
+    if (F::MONTGOMERY) F::nres(a, w); else F::nres(a, t);
+    return lt;
   }
 
   // modexp, pseudo.py:1115-1127: canonical plain value as words, least significant first
@@ -181,12 +191,7 @@ template <class F> struct Field {
     (void)F::canon(w, w);
   }
   // modimp, pseudo.py:1130-1146: raw words (value < 2^(32L)) -> stored form; returns 1 iff < p
-  static MAB_DEV uint32_t from_words(uint32_t (&a)[L], const uint32_t (&w)[L]) {
-    uint32_t t[L];
-    uint32_t lt = F::canon(t, w);
-    F::nres(a, t);
-    return lt;
-  }
+  static MAB_DEV uint32_t from_words(uint32_t (&a)[L], const uint32_t (&w)[L]) { return import_raw(a, w); }
   // modsign, pseudo.py:1149-1158; modcmp, pseudo.py:1161-1174
   static MAB_DEV uint32_t sign(const uint32_t (&a)[L]) {
     uint32_t c[L];

@@ -128,12 +128,18 @@ template <class F, int K> __global__ void __launch_bounds__(128) k_inv_shared(Ma
     F::pro(h, P[K - 1]);
     Fd::template inv<true>(acc, P[K - 1], h);
   }
+  // The bound is re-read behind a compiler barrier: ptxas otherwise keeps the K comparisons of the first loop
+  // alive across the whole inversion by packing them into the register that also holds the (secret) zero flags,
+  // and branches on bits of that register -- correct, but impossible to tell from a secret-dependent branch in
+  // the SASS (tools/ct_audit.py).
+  size_t nn = p.n;
+  asm volatile("" : "+l"(nn));
 #pragma unroll
   for (int j = K - 1; j >= 0; j--) {
     const size_t i = first + (size_t)j * blockDim.x;
     uint32_t r[L];
     if (j > 0) {
-      if (i < p.n) plane_ld<L>(a, p.a, p.stride, i); else Fd::cpy(a, one);
+      if (i < nn) plane_ld<L>(a, p.a, p.stride, i); else Fd::cpy(a, one);
       Fd::cmv((flags >> j) & 1u, one, a);
       F::mul(r, acc, P[j - 1]);
       F::mul(acc, acc, a);
@@ -143,7 +149,7 @@ template <class F, int K> __global__ void __launch_bounds__(128) k_inv_shared(Ma
     uint32_t zero[L];
     Fd::zer(zero);
     Fd::cmv((flags >> j) & 1u, zero, r);
-    if (i < p.n) plane_st<L>(p.r, p.stride, i, r);
+    if (i < nn) plane_st<L>(p.r, p.stride, i, r);
   }
 }
 
@@ -270,33 +276,91 @@ template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k
 }
 
 // rfc7748 with the inversions of up to four keys per thread shared (Rfc7748<F>::finish_batch).
-// Persistent grid (one launch fills the GPU exactly); each warp repeatedly takes the next CHUNK of
-// 32*K consecutive keys from an atomic counter and every thread runs K ladders back to back before one
-// shared inversion.  The chunk list is fixed by the host: K = 4 chunks first, then K = 2, then K = 1, the
-// small ones last so that warps the scheduler favoured (they run ahead: the sub-partition arbiter is not
-// fair) pick up more of them and all warps finish together.
+// Persistent grid (one launch fills the GPU exactly); a warp repeatedly takes the next CHUNK of K
+// consecutive 32-key groups and every thread runs K ladders back to back before one shared inversion.
+//
+// Work distribution: the G groups of the batch are cut into `nq` equal contiguous QUEUES.  With the full
+// persistent grid nq = SMs x 4 and a warp serves the queue of the sub-partition it runs on (%smid, warp
+// index: a 128-thread CTA puts warp w on sub-partition w), so every sub-partition is handed the same
+// amount of work whatever the batch size -- the multiplier pipe of a sub-partition is the resource, and a
+// batch of 1.7 rounds that lets some sub-partitions run two full rounds while others idle loses 13 %
+// (round 1: 0.87 of the large-batch rate at 2^17 keys).  Inside a queue the resident warps draw chunks
+// from an atomic counter: K = 4 chunks first, then K = 2, single groups last, so that the warps the
+// scheduler favoured (the sub-partition arbiter is not fair) take more of them and all finish together.
+// A warp whose queue is empty steals from the other queues, which also makes the result independent of
+// where the CTAs were placed.  Small batches (grid below full residency) use one queue.
 #define MAB_LADDER_KMAX 4
-struct MabChunks {
-  unsigned long long* counter;     // zeroed before the launch
-  unsigned c4, c2;                 // number of K=4 chunks, then of K=2 chunks; K=1 chunks follow up to n
+struct MabQueues {
+  unsigned long long* counter;     // nq counters, zeroed before the launch
+  unsigned nq;                     // number of queues
+  unsigned sms;                    // SMs the grid was sized for (nq == 4 * sms, or nq == 1)
+  // The G groups are cut into nq contiguous queues of `base` groups, the first `rem` of them one longer.  The
+  // chunk list of a queue (see mab_queue_chunks on the host side) depends on its length only, so the host works
+  // it out for the two lengths that occur: index 0 = base groups, index 1 = base + 1.
+  unsigned base, rem;
+  unsigned c4s, c2s, c4l, c2l;     // K = 4 chunks, then K = 2 chunks (s: base groups, l: base + 1); single groups follow
 };
-template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align, MabChunks ch) {
+// groups [lo, lo + g) of queue q; `longer` = 1 for the queues that hold base + 1 groups
+static __device__ __forceinline__ void mab_queue_range(const MabQueues& Q, unsigned q, unsigned long long& lo, unsigned& g, unsigned& longer) {
+  longer = q < Q.rem ? 1u : 0u;
+  lo = (unsigned long long)q * Q.base + (q < Q.rem ? q : Q.rem);
+  g = Q.base + longer;
+}
+// chunk ci of a queue: returns K (0 = past the end) and the first group of the chunk inside the queue
+static __device__ __forceinline__ int mab_queue_chunk(unsigned g, unsigned c4, unsigned c2, unsigned long long ci, unsigned& first) {
+  if (ci < c4) { first = (unsigned)ci * 4; return 4; }
+  if (ci < (unsigned long long)c4 + c2) { first = c4 * 4 + (unsigned)(ci - c4) * 2; return 2; }
+  const unsigned long long s = (unsigned long long)c4 * 4 + (unsigned long long)c2 * 2 + (ci - c4 - c2);
+  if (s >= g) return 0;
+  first = (unsigned)s;
+  return 1;
+}
+template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align, MabQueues Q) {
   constexpr int L = F::L;
   constexpr int T = MAB_LADDER_THREADS;
   extern __shared__ uint32_t mab_smem[];
   uint32_t* st = mab_smem + threadIdx.x;                               // K slots x 3 elements x L words
   uint32_t* stash = F::LADDER_STASH ? (mab_smem + MAB_LADDER_KMAX * 3 * L * T + threadIdx.x) : nullptr;
   const unsigned lane = threadIdx.x & 31;
+  unsigned home = 0;
+  if (Q.nq > 1) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    while (smid >= Q.sms) smid -= Q.sms;            // sparse SM numbering: fold (any mapping is correct)
+    home = smid * 4 + ((threadIdx.x >> 5) & 3);
+  }
+  unsigned q = home, visited = 0;
   for (;;) {
-    unsigned long long ci = 0;
-    if (lane == 0) ci = atomicAdd(ch.counter, 1ULL);
-    ci = __shfl_sync(0xffffffffu, ci, 0);
-    int K;
-    size_t start;
-    if (ci < ch.c4) { K = 4; start = (size_t)ci * 128; }
-    else if (ci < (unsigned long long)ch.c4 + ch.c2) { K = 2; start = (size_t)ch.c4 * 128 + (size_t)(ci - ch.c4) * 64; }
-    else { K = 1; start = (size_t)ch.c4 * 128 + (size_t)ch.c2 * 64 + (size_t)(ci - ch.c4 - ch.c2) * 32; }
-    if (start >= n) break;
+    // next chunk: from the current queue, else move on to the next queue (each queue is left for good once
+    // it is seen empty: its counter only grows)
+    int K = 0;
+    unsigned first = 0;
+    unsigned long long glo = 0;
+    while (visited < Q.nq) {
+      unsigned g, longer;
+      mab_queue_range(Q, q, glo, g, longer);
+      unsigned long long ci = 0;
+      const unsigned c4 = longer ? Q.c4l : Q.c4s, c2 = longer ? Q.c2l : Q.c2s;
+      const unsigned nchunks = c4 + c2 + (g - 4 * c4 - 2 * c2);
+      int ok = 0;
+      if (lane == 0) {
+        // a plain read first: an exhausted queue costs a load, not an atomic
+        if (*(volatile unsigned long long*)(Q.counter + q) < (unsigned long long)nchunks) {
+          ci = atomicAdd(Q.counter + q, 1ULL);
+          ok = 1;
+        }
+      }
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      if (ok) {
+        ci = __shfl_sync(0xffffffffu, ci, 0);
+        K = mab_queue_chunk(g, c4, c2, ci, first);
+        if (K) break;
+      }
+      q = (q + 1 == Q.nq) ? 0 : q + 1;
+      visited++;
+    }
+    if (!K) break;
+    const size_t start = (size_t)(glo + first) * 32;
     MAB_NOUNROLL
     for (int j = 0; j < K; j++) {
       const size_t idx = start + (size_t)j * 32 + lane;

@@ -121,27 +121,52 @@ int mab_host_workspace_acquire(int device, size_t bytes, MabWorkspace** out) {
 void mab_host_workspace_release(MabWorkspace* ws) { g_ws_mutex[ws->device].unlock(); }
 
 // ---- work counters of the persistent ladder kernels --------------------------------------------------
-#define MAB_NCOUNTERS 1024
+#define MAB_NSLOTS 256
+struct MabCounterSlot {
+  cudaEvent_t done;        // recorded behind the last kernel that used the slot
+  bool used;
+};
 static unsigned long long* g_counters[MAB_WS_MAXDEV];
+static MabCounterSlot* g_slots[MAB_WS_MAXDEV];
 static unsigned g_counter_next[MAB_WS_MAXDEV];
 static std::mutex g_counter_mutex;
 
-int mab_chunk_counter(cudaStream_t stream, unsigned long long** out) {
+int mab_queue_counters(cudaStream_t stream, unsigned nq, unsigned long long** out, int* slot) {
+  if (nq == 0 || nq > MAB_QUEUE_MAX) return MAB_ERR_BADARG;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
   if (dev < 0 || dev >= MAB_WS_MAXDEV) return MAB_ERR_BADARG;
-  unsigned long long* slot;
+  unsigned id;
   {
     std::lock_guard<std::mutex> g(g_counter_mutex);
     if (!g_counters[dev]) {
-      if ((e = cudaMalloc((void**)&g_counters[dev], MAB_NCOUNTERS * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+      if ((e = cudaMalloc((void**)&g_counters[dev], (size_t)MAB_NSLOTS * MAB_QUEUE_MAX * sizeof(unsigned long long))) != cudaSuccess) return (int)e;
+      g_slots[dev] = new MabCounterSlot[MAB_NSLOTS];
+      for (int i = 0; i < MAB_NSLOTS; i++) {
+        g_slots[dev][i].used = false;
+        if ((e = cudaEventCreateWithFlags(&g_slots[dev][i].done, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+      }
     }
-    slot = g_counters[dev] + (g_counter_next[dev]++ % MAB_NCOUNTERS);
+    id = g_counter_next[dev]++ % MAB_NSLOTS;
+    // the previous user of this slot (MAB_NSLOTS launches ago, possibly on another stream) must have finished
+    if (g_slots[dev][id].used && (e = cudaStreamWaitEvent(stream, g_slots[dev][id].done, 0)) != cudaSuccess) return (int)e;
+    g_slots[dev][id].used = true;
   }
-  if ((e = cudaMemsetAsync(slot, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return (int)e;
-  *out = slot;
+  unsigned long long* p = g_counters[dev] + (size_t)id * MAB_QUEUE_MAX;
+  if ((e = cudaMemsetAsync(p, 0, (size_t)nq * sizeof(unsigned long long), stream)) != cudaSuccess) return (int)e;
+  *out = p;
+  *slot = (int)id;
   return 0;
+}
+
+int mab_queue_counters_launched(int slot, cudaStream_t stream) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= MAB_WS_MAXDEV || slot < 0 || slot >= MAB_NSLOTS || !g_slots[dev]) return MAB_ERR_BADARG;
+  std::lock_guard<std::mutex> g(g_counter_mutex);
+  return (int)cudaEventRecord(g_slots[dev][slot].done, stream);
 }
 
 // ---- stream-ordered scratch pool (table slices of the scalar multiplication kernels) -------------------

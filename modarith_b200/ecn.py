@@ -43,8 +43,16 @@ def _args(curve, arrays):
 def _call(name, arrays, on_device, xo, yo):
     lib = _lib.load()
     e = arrays[0]
-    xo = torch.empty_like(e) if xo is None or not on_device else xo
-    yo = torch.empty_like(e) if yo is None or not on_device else yo
+    if not on_device and (xo is not None or yo is not None):
+        raise ValueError("xo / yo can only be supplied with device tensors (host arguments get fresh numpy results)")
+    for nm, t in (("xo", xo), ("yo", yo)):
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.uint8 or t.shape != e.shape \
+                or t.device != e.device or not t.is_contiguous():
+            raise ValueError("%s must be a contiguous uint8 CUDA tensor of shape %s on %s" % (nm, tuple(e.shape), e.device))
+    xo = torch.empty_like(e) if xo is None else xo
+    yo = torch.empty_like(e) if yo is None else yo
     stream = torch.cuda.current_stream(e.device).cuda_stream
     with torch.cuda.device(e.device):
         _lib.check(getattr(lib, name)(*(t.data_ptr() for t in arrays), xo.data_ptr(), yo.data_ptr(), e.shape[0], stream), name)

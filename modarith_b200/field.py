@@ -45,8 +45,10 @@ class Field:
 
     def _call(self, name, lead, planes):
         """planes: a tensor defining n/stride."""
-        assert planes.dtype == torch.int32 and planes.dim() == 2 and planes.shape[0] == self.Nlimbs
-        assert planes.stride(1) == 1, "limb planes must be contiguous along the element axis"
+        if planes.dtype != torch.int32 or planes.dim() != 2 or planes.shape[0] != self.Nlimbs:
+            raise ValueError("expected int32 limb planes [%d, n]" % self.Nlimbs)
+        if planes.shape[1] > 1 and planes.stride(1) != 1:
+            raise ValueError("limb planes must be contiguous along the element axis")
         n, stride = planes.shape[1], planes.stride(0) if planes.shape[1] > 0 else 0
         stream = torch.cuda.current_stream(self.device).cuda_stream
         fn = getattr(self.lib, "mab_%s_%s" % (self.prime, name))
@@ -58,13 +60,30 @@ class Field:
         for t in ts:
             if t is None:
                 continue
-            assert t.is_cuda and t.dtype == torch.int32 and t.dim() == 2 and t.shape[0] == self.Nlimbs, \
-                "expected int32 limb planes [Nlimbs, n] on the GPU"
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise TypeError("field elements are CUDA tensors (int32 limb planes [%d, n])" % self.Nlimbs)
+            if t.dtype != torch.int32 or t.dim() != 2 or t.shape[0] != self.Nlimbs:
+                raise ValueError("expected int32 limb planes [%d, n] on the GPU, got %s %s" % (self.Nlimbs, t.dtype, tuple(t.shape)))
+            if t.device != self.device:
+                raise ValueError("operand lives on %s, this Field on %s" % (t.device, self.device))
             if ref is None:
                 ref = t
-            else:
-                assert t.shape == ref.shape and t.stride() == ref.stride(), "operands must share shape and pitch"
+            elif t.shape != ref.shape or t.stride() != ref.stride():
+                raise ValueError("operands must share shape and pitch")
         return ref
+
+    def _bits(self, b, g):
+        if not isinstance(b, torch.Tensor) or not b.is_cuda or b.dtype != torch.int32 or b.shape != (g.shape[1],) \
+                or not b.is_contiguous():
+            raise ValueError("swap / move bits must be a contiguous int32 CUDA tensor of shape [n]")
+
+    def _bytes(self, b, n, name):
+        if not isinstance(b, torch.Tensor) or not b.is_cuda or b.dtype != torch.uint8:
+            raise TypeError("%s must be a uint8 CUDA tensor" % name)
+        if b.dim() != 2 or b.shape[1] != self.Nbytes or (n is not None and b.shape[0] != n) or not b.is_contiguous():
+            raise ValueError("%s must be a contiguous [n, %d] byte array" % (name, self.Nbytes))
+        if b.device != self.device:
+            raise ValueError("%s lives on %s, this Field on %s" % (name, b.device, self.device))
 
     # -- the generated-code API (reference argument order) ------------------------------------
     def modfsb(self, n_):
@@ -144,11 +163,11 @@ class Field:
         self._call("redc", [_ptr(n_), _ptr(m)], self._chk(n_, m))
 
     def modcsw(self, b, g, f):
-        assert b.dtype == torch.int32 and b.shape == (g.shape[1],)
+        self._bits(b, g)
         self._call("modcsw", [_ptr(b), _ptr(g), _ptr(f)], self._chk(g, f))
 
     def modcmv(self, b, g, f):
-        assert b.dtype == torch.int32 and b.shape == (g.shape[1],)
+        self._bits(b, g)
         self._call("modcmv", [_ptr(b), _ptr(g), _ptr(f)], self._chk(g, f))
 
     def modshl(self, n: int, a):
@@ -169,13 +188,13 @@ class Field:
         n = a.shape[1]
         if b is None:
             b = torch.empty((n, self.Nbytes), dtype=torch.uint8, device=self.device)
-        assert b.is_contiguous() and b.shape == (n, self.Nbytes) and b.dtype == torch.uint8
+        self._bytes(b, n, "b")
         self._call("modexp", [_ptr(a), _ptr(b)], self._chk(a))
         return b
 
     def modimp(self, b, a=None):
         """b: [n, Nbytes] uint8 big-endian.  Returns (planes, status) with status[i]=1 iff < p."""
-        assert b.is_cuda and b.dtype == torch.uint8 and b.dim() == 2 and b.shape[1] == self.Nbytes and b.is_contiguous()
+        self._bytes(b, None, "b")
         n = b.shape[0]
         if a is None:
             a = self.alloc(n)

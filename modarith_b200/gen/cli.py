@@ -53,5 +53,7 @@ def main(family: str, argv) -> int:
     return 0
 
 
-def generate_all(verbose=False):
-    return [generate(P, verbose=verbose) for P in ALL_PRIMES.values()]
+def generate_all(verbose=False, outdir=None):
+    """Headers of every built-in modulus; into csrc/gen (the committed copies) or, for tests, into `outdir`/gen."""
+    return [generate(P, None if outdir is None else os.path.join(outdir, "gen", "field_%s.cuh" % P.name), verbose=verbose)
+            for P in ALL_PRIMES.values()]

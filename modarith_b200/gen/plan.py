@@ -194,6 +194,37 @@ class Plan:
             assert r < B and r % p == (-x) % p, ("neg", hex(x))
             r, e = self.run("canon", a=ax)
             assert r == x % p and e["lt"] == (1 if x < p else 0), ("canon", hex(x))
+        # raw imports (modimp / mod2r hand over any value below 2^(32L), Field::import_raw): plain-residue plans
+        # canonicalise it, Montgomery plans multiply the raw words by R^2 and rely on the product's own reduction
+        top = 1 << (32 * L)
+        raw = [top - 1, top - 2, p, p + 1, 2 * p - 1, 2 * p, 2 * p + 1, 3 * p, top >> 1, (top >> 1) + 1]
+        raw = [v for v in raw if 0 <= v < top] + [rng.randrange(top) for _ in range(40)]
+        for x in raw:
+            ax = words(x, L)
+            r, e = self.run("canon", a=ax)
+            assert e["lt"] == (1 if x < p else 0), ("canon flag", hex(x))
+            if self.R == 1:
+                assert r == x % p, ("canon over the raw range", hex(x))
+            else:
+                r, _ = self.run("mul", a=ax, b=words(self.R * self.R % p, L))
+                assert r == x * self.R % p, ("raw import through R^2", hex(x))
+        # every pair of edge values through mul / add / sub (the shuffled pairing above does not guarantee that
+        # the extremes meet: B-1 times B-1 is what stresses the last wrap of a fold)
+        edge = [v for v in xs[:60] if v in (0, 1, 2, p - 1, p, p + 1, B - 1, B - 2, 2 * p - 1) or v >= B - (1 << 40)]
+        edge = sorted(set(edge + [B - 1, p - 1, 0, 1]))[:14]
+        for x in edge:
+            for y in edge:
+                if x >= B or y >= B:
+                    continue
+                ax, ay = words(x, L), words(y, L)
+                r, _ = self.run("mul", a=ax, b=ay)
+                assert r < B and r % p == x * y * Rinv % p, ("mul", hex(x), hex(y))
+                r, _ = self.run("add", a=ax, b=ay)
+                assert r < B and r % p == (x + y) % p, ("add", hex(x), hex(y))
+                r, _ = self.run("sub", a=ax, b=ay)
+                assert r < B and r % p == (x - y) % p, ("sub", hex(x), hex(y))
+                r, _ = self.run("mla", a=ax, c=ay, b=M32 >> 1)
+                assert r < B and r % p == (x * (M32 >> 1) + y) % p, ("mla", hex(x), hex(y))
         if self.tight:
             # mul/sqr land below the tight bound for ANY stored operands; add_tt/sub_tt are exact on tight operands
             T = self.tight
@@ -469,6 +500,163 @@ class PseudoMersenne(Plan):
         if self.bound > 3 * self.p:
             r = self._cond_sub_p(asm, r)
         self._outs(asm, r)
+        asm.out("lt", lt)
+        return asm
+
+
+class PseudoMersenne33(Plan):
+    """2^(32L) - c with c = 2^32 + cl, cl < 2^15 (secp256k1's field: c = 2^32 + 977), on L saturated limbs;
+    stored values are any representative < 2^(32L) (< 2p), plain residues (R = 1).
+
+    The reference builds this modulus through monty.py (Montgomery form, monty.py:2066-2067: "not exploitable"
+    for its unsaturated radix); with saturated limbs the shape is: 2^(32L) == c, so a double-length product
+    folds as lo + cl*hi + (hi << 32) -- L wide multiplies by the small constant on the even/odd accumulator
+    windows (as in PseudoMersenne._fold_split) plus one word-shifted add chain -- then the word and a bit that
+    stick out above 2^(32L) fold once more (one wide multiply), and a last wrap can only add c to a value that
+    is tiny by then.  L^2 + L + 1 wide multiplies per modmul against 2 L^2 + L for the word-serial Montgomery
+    fall-back this modulus used before."""
+    family = "monty"
+
+    def __init__(self, prime):
+        super().__init__(prime)
+        n, L = prime.nbits, self.L
+        assert n == 32 * L and L % 2 == 0
+        self.c = (1 << n) - prime.p
+        self.cl = self.c - (1 << 32)
+        assert 0 < self.cl < (1 << 15), "modulus is not 2^(32L) - 2^32 - small"
+        assert self.bound <= 2 * self.p
+
+    # -- folding what sticks out above 2^(32L) ----------------------------------------------------------
+    def _fold_word(self, asm, r, t0, t1=None):
+        """r (L words) + (t0 + 2^32*t1) * 2^(32L) -> L words, for a 32-bit word t0 and an optional bit t1:
+        t*c = t*cl + (t << 32) is at most three words; one add chain, then a wrap can only happen onto a value
+        below 2^67, where adding c once more stays inside three words."""
+        L, cl = self.L, self.cl
+        p0, p1 = asm.tmp(), asm.tmp()
+        asm.mullo(p0, t0, cl)
+        asm.mulhi(p1, t0, cl)                          # < cl
+        if t1 is not None:
+            q1 = asm.tmp()
+            asm.madlo(q1, t1, cl, p1)                  # + t1*cl*2^32, cannot overflow (p1 < cl, t1 <= 1)
+            p1 = q1
+        v1, v2 = asm.tmp(), asm.tmp()
+        asm.add(v1, p1, t0, cout=True)                 # + (t << 32): t0 at word 1, t1 at word 2
+        asm.add(v2, t1 if t1 is not None else 0, 0, cin=True)
+        o = asm.tmp(L)
+        c2 = asm.tmp()
+        asm.add_chain(o, r, [p0, v1, v2] + [0] * (L - 3), carry_to=(c2, 0))
+        f0 = asm.tmp()
+        asm.madlo(f0, c2, cl, o[0], cout=True)         # wrapped: o < 2^67, so o + c fits in three words
+        f1, f2 = asm.tmp(), asm.tmp()
+        asm.add(f1, o[1], c2, cin=True, cout=True)
+        asm.add(f2, o[2], 0, cin=True)
+        return [f0, f1, f2] + o[3:]
+
+    def _fold_double(self, asm, lo_even, hi, lo_odd=None):
+        """lo_even + 2^32*lo_odd + c*hi -> L words (hi: L words)."""
+        L, cl = self.L, self.cl
+        r = asm.tmp(L)
+        ce = asm.tmp()
+        ev = [(r[k], r[k + 1], hi[k], cl, lo_even[k], lo_even[k + 1]) for k in range(0, L, 2)]
+        asm.wide_chain(ev, last_carry_to=(ce, 0))
+        o = {k: asm.tmp() for k in range(1, L + 1)}
+        if lo_odd is None:
+            for k in range(1, L, 2):
+                asm.mullo(o[k], hi[k], cl)
+                asm.mulhi(o[k + 1], hi[k], cl)
+        else:
+            od = [(o[k], o[k + 1], hi[k], cl, lo_odd[k], lo_odd[k + 1] if k + 1 < L else 0) for k in range(1, L, 2)]
+            asm.wide_chain(od, last_carry_to=None)
+        res = [r[0]] + asm.tmp(L - 1)
+        top = asm.tmp()
+        for k in range(1, L):
+            asm.add(res[k], r[k], o[k], cin=(k > 1), cout=True)
+        asm.add(top, ce, o[L], cin=True, cout=False)               # lo + cl*hi = res + top*2^(32L), top <= cl
+        # + (hi << 32): hi[k-1] onto word k, hi[L-1] onto the word above
+        s = [res[0]] + asm.tmp(L - 1)
+        for k in range(1, L):
+            asm.add(s[k], res[k], hi[k - 1], cin=(k > 1), cout=True)
+        t0, t1 = asm.tmp(), asm.tmp()
+        asm.add(t0, top, hi[L - 1], cin=True, cout=True)
+        asm.add(t1, 0, 0, cin=True)
+        return self._fold_word(asm, s, t0, t1)
+
+    def reduce_wide(self, asm, T):
+        L = self.L
+        return self._fold_double(asm, T[:L], T[L:], None)
+
+    def reduce_small(self, asm, T):
+        return self._fold_word(asm, T[:self.L], T[self.L])
+
+    def build_mul(self):
+        asm = Asm(self.name + ".mul")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        E, O = satmul.product_eo(asm, a, b)
+        U = asm.tmp(L)
+        for k in range(L):
+            asm.add(U[k], E.src(L + k), O.src(L + k), cin=(k > 0), cout=(k < L - 1))
+        lo_even = [E.src(k) for k in range(L)]
+        lo_odd = {k: O.src(k) for k in range(1, L)}
+        self._outs(asm, self._fold_double(asm, lo_even, U, lo_odd))
+        return asm
+
+    def build_add(self):
+        asm = Asm(self.name + ".add")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        s = asm.tmp(L)
+        c = asm.tmp()
+        asm.add_chain(s, a, b, carry_to=(c, 0))
+        self._outs(asm, self._fold_bit(asm, s, c))
+        return asm
+
+    def _fold_bit(self, asm, r, c):
+        """r + c*2^(32L) for a bit c: add c*(2^32 + cl); a second wrap leaves a value below 2^34."""
+        L, cl = self.L, self.cl
+        f = asm.tmp()
+        asm.madlo(f, c, cl, 0)
+        o = asm.tmp(L)
+        c2 = asm.tmp()
+        asm.add_chain(o, r, [f, c] + [0] * (L - 2), carry_to=(c2, 0))
+        g = asm.tmp()
+        asm.madlo(g, c2, cl, 0)
+        h0, h1 = asm.tmp(), asm.tmp()
+        asm.add(h0, o[0], g, cout=True)
+        asm.add(h1, o[1], c2, cin=True)
+        return [h0, h1] + o[2:]
+
+    def build_sub(self, neg):
+        asm = Asm(self.name + (".neg" if neg else ".sub"))
+        L, cl = self.L, self.cl
+        if neg:
+            (b,) = self._io(asm, ["b"])
+            a = [0] * L
+        else:
+            a, b = self._io(asm, ["a", "b"])
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)           # value = d - 2^(32L)*[m] == d - c*[m]
+        f, b1 = asm.tmp(), asm.tmp()
+        asm.logic("and", f, m, cl)
+        asm.logic("and", b1, m, 1)
+        e = asm.tmp(L)
+        m2 = asm.tmp()
+        asm.sub_chain(e, d, [f, b1] + [0] * (L - 2), borrow_to=m2)
+        f2, b2 = asm.tmp(), asm.tmp()
+        asm.logic("and", f2, m2, cl)
+        asm.logic("and", b2, m2, 1)
+        g0, g1 = asm.tmp(), asm.tmp()
+        asm.sub(g0, e[0], f2, cout=True)              # after a second borrow e >= 2^(32L) - c: no third one
+        asm.sub(g1, e[1], b2, cin=True)
+        self._outs(asm, [g0, g1] + e[2:])
+        return asm
+
+    def build_canon(self):
+        asm = Asm(self.name + ".canon")
+        (a,) = self._io(asm, ["a"])
+        lt = asm.tmp()
+        self._outs(asm, self._cond_sub_p(asm, a, want_flag=lt))
         asm.out("lt", lt)
         return asm
 
@@ -868,6 +1056,8 @@ def make_plan(prime: Prime) -> Plan:
         cands.append(GenMersenne)
     if L % 2 == 0 and c < (1 << 12) and (c << (32 * L - n)) < (1 << 15):
         cands.append(PseudoMersenne)
+    if L % 2 == 0 and n == 32 * L and 0 < c - (1 << 32) < (1 << 15):
+        cands.append(PseudoMersenne33)
     cands += [Montgomery, MontgomeryFull]
     err = None
     for cls in cands:

@@ -108,9 +108,10 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, "mab_%s_rfc7748_validate" % P)
         fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
         fn.restype = c_int
-        fn = getattr(lib, "mab_%s_rfc7748_host" % P)
-        fn.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int]
-        fn.restype = c_int
+        for name in ("mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_host_multi" % P):
+            fn = getattr(lib, name)
+            fn.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int]
+            fn.restype = c_int
     _lib = lib
     return lib
 
@@ -124,7 +125,7 @@ def exported_symbols():
         syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
     for P in CURVES:
         syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_validate" % P,
-                 "mab_%s_rfc7748_perkey" % P]
+                 "mab_%s_rfc7748_perkey" % P, "mab_%s_rfc7748_host_multi" % P]
     return syms
 
 

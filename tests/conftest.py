@@ -16,6 +16,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Plain `pytest` on a box without a GPU: the gpu-marked tests are skipped, not failed (on a GPU box they run;
+    the product itself never falls back -- see tests/test_abi.py)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_rfc():
     with open(os.path.join(ROOT, "tests", "golden", "rfc7748.json")) as f:
@@ -51,9 +67,10 @@ def hostsim(tmp_path_factory):
     """g++ build of the generated headers + device templates with the PTX blocks transcribed to C
     (tests/hostsim/hostsim.cpp).  Test scaffolding: lets the CPU suite run the device logic."""
     from modarith_b200.gen.cli import generate_all
-    generate_all(verbose=False)
-    out = str(tmp_path_factory.mktemp("hostsim") / "libhostsim.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w",
+    d = tmp_path_factory.mktemp("hostsim")
+    generate_all(verbose=False, outdir=str(d))           # fresh headers in a scratch directory, not in the source tree
+    out = str(d / "libhostsim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I", str(d),
                            "-I", os.path.join(ROOT, "modarith_b200", "csrc"),
                            "-o", out, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     return ctypes.CDLL(out)

@@ -5,7 +5,8 @@ import random
 import pytest
 
 from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime
-from modarith_b200.gen.plan import make_plan, PseudoMersenne, GenMersenne, Montgomery, MontgomeryFull, words, value
+from modarith_b200.gen.plan import (make_plan, PseudoMersenne, PseudoMersenne33, GenMersenne, Montgomery, MontgomeryFull,
+                                    words, value)
 from modarith_b200.gen.ptx import Asm, LostCarry
 from modarith_b200.gen import satmul
 from modarith_b200.gen.emit import emit_field_header
@@ -34,7 +35,7 @@ def test_product_counts(name):
     plan = make_plan(PRIMES[name])
     b = plan.build()
     L = plan.L
-    fold = L if name == "X25519" else 0
+    fold = L if name == "X25519" else (L + 1 if isinstance(plan, PseudoMersenne33) else 0)
     if isinstance(plan, MontgomeryFull):      # separated-operand REDC: + L(L+1)/2 - L (low half) + L^2 (Q*p)
         assert b["mul"].stats()[0] <= L * L + L * (L + 1) // 2 + L * L
         return
@@ -92,7 +93,8 @@ def test_emitted_header_is_reproducible(name):
 def test_fallback_plan_accepts_any_odd_modulus():
     """Every kind of prime the reference's named tables hold gets a plan that passes the bignum
     self-check: odd limb counts, unshaped Montgomery moduli, group orders (monty.py:1961-2127)."""
-    assert isinstance(make_plan(PRIMES["SECP256K1"]), MontgomeryFull)
+    assert isinstance(make_plan(PRIMES["SECP256K1"]), PseudoMersenne33)       # 2^256 - 2^32 - 977: shaped after all
+    assert MontgomeryFull(PRIMES["SECP256K1"]).build() and MontgomeryFull(PRIMES["SECP256K1"]).L == 8
     assert isinstance(make_plan(PRIMES["NIST256ORDER"]), MontgomeryFull)
     for nm, p in {"NIST384": 2**384 - 2**128 - 2**96 + 2**32 - 1, "NIST521": 2**521 - 1, "PM266": 2**266 - 3,
                   "NIST224": 2**224 - 2**96 + 1, "GM480": 2**480 - 2**240 - 1,

@@ -6,11 +6,12 @@ OUT=gpurun_out/sweep_n$N.jsonl
 : > $OUT
 for LG in ${SWEEP_LGS:-20 22 24 26 28}; do
   PER=$(( (1 << LG) / N ))
+  PK=$(( 1048576 / N ))          # a fixed 2^20 sub-sample of every run is compared with the reference build
   if [ "$N" = "1" ]; then
-    python bench.py --gpus 1 --steps 3 --warmup 3 --keys $PER --no-extra --no-cpu-baseline --parity-keys 65536 >> $OUT
+    python bench.py --gpus 1 --steps 3 --warmup 3 --keys $PER --no-extra --no-cpu-baseline --parity-keys $PK >> $OUT
   else
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
-      bench.py --gpus $N --steps 3 --warmup 3 --keys $PER --no-extra --no-cpu-baseline --parity-keys 65536 2>/dev/null | tail -1 >> $OUT
+      bench.py --gpus $N --steps 3 --warmup 3 --keys $PER --no-extra --no-cpu-baseline --parity-keys $PK 2>/dev/null | tail -1 >> $OUT
   fi
 done
 python - <<PY
