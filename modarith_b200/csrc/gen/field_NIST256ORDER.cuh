@@ -4049,6 +4049,11 @@ struct F_NIST256ORDER {
   static MAB_DEV void add_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { add(r, a, b); }
   static MAB_DEV void sub_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { sub(r, a, b); }
 
+  // no separate weakly-reduced products in this plan: chains use the ordinary ones
+  static constexpr bool WEAK = false;
+  static MAB_DEV void mul_w(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { mul(r, a, b); }
+  static MAB_DEV void sqr_w(uint32_t (&r)[8], const uint32_t (&a)[8]) { sqr(r, a); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[8], const uint32_t (&b)[8]) {
 #ifndef MAB_HOSTSIM
@@ -4260,164 +4265,165 @@ struct F_NIST256ORDER {
     uint32_t t1[L];
     uint32_t t2[L];
     uint32_t t3[L];
-    sqr(t0, x);
-    mul(t0, t0, x);
-    sqr(t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t2, t1);
+    sqr_w(t0, x);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t2, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(t2, t2);
-    mul(t2, t2, t1);
-    sqr(t3, t2);
+    for (int i = 1; i < 4; i++) sqr_w(t2, t2);
+    mul_w(t2, t2, t1);
+    sqr_w(t3, t2);
     MAB_NOUNROLL
-    for (int i = 1; i < 8; i++) sqr(t3, t3);
-    mul(t3, t3, t2);
-    sqr(t2, t3);
+    for (int i = 1; i < 8; i++) sqr_w(t3, t3);
+    mul_w(t3, t3, t2);
+    sqr_w(t2, t3);
     MAB_NOUNROLL
-    for (int i = 1; i < 16; i++) sqr(t2, t2);
-    mul(t2, t2, t3);
-    sqr(z, t2);
+    for (int i = 1; i < 16; i++) sqr_w(t2, t2);
+    mul_w(t2, t2, t3);
+    sqr_w(z, t2);
     MAB_NOUNROLL
-    for (int i = 1; i < 64; i++) sqr(z, z);
-    mul(z, z, t2);
-    sqr(z, z);
+    for (int i = 1; i < 64; i++) sqr_w(z, z);
+    mul_w(z, z, t2);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 32; i++) sqr(z, z);
-    mul(z, z, t2);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 32; i++) sqr_w(z, z);
+    mul_w(z, z, t2);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 6; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 6; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 6; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
+    for (int i = 1; i < 6; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 4; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 4; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, t0);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
-    sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
+    if (WEAK) (void)canon(z, z);
   }
 };

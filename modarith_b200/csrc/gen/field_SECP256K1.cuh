@@ -1251,6 +1251,11 @@ struct F_SECP256K1 {
   static MAB_DEV void add_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { add(r, a, b); }
   static MAB_DEV void sub_tt(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { sub(r, a, b); }
 
+  // no separate weakly-reduced products in this plan: chains use the ordinary ones
+  static constexpr bool WEAK = false;
+  static MAB_DEV void mul_w(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { mul(r, a, b); }
+  static MAB_DEV void sqr_w(uint32_t (&r)[8], const uint32_t (&a)[8]) { sqr(r, a); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[8], const uint32_t (&b)[8]) {
 #ifndef MAB_HOSTSIM
@@ -1468,63 +1473,64 @@ struct F_SECP256K1 {
     uint32_t t3[L];
     uint32_t t4[L];
     uint32_t t5[L];
-    sqr(t0, x);
-    mul(t0, t0, x);
-    sqr(t1, t0);
-    mul(t1, t1, x);
-    sqr(t2, t1);
+    sqr_w(t0, x);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
+    mul_w(t1, t1, x);
+    sqr_w(t2, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(t2, t2);
-    mul(t2, t2, t1);
-    sqr(t3, t2);
+    for (int i = 1; i < 3; i++) sqr_w(t2, t2);
+    mul_w(t2, t2, t1);
+    sqr_w(t3, t2);
     MAB_NOUNROLL
-    for (int i = 1; i < 6; i++) sqr(t3, t3);
-    mul(t3, t3, t2);
-    sqr(t3, t3);
-    mul(t3, t3, x);
-    sqr(t4, t3);
+    for (int i = 1; i < 6; i++) sqr_w(t3, t3);
+    mul_w(t3, t3, t2);
+    sqr_w(t3, t3);
+    mul_w(t3, t3, x);
+    sqr_w(t4, t3);
     MAB_NOUNROLL
-    for (int i = 1; i < 13; i++) sqr(t4, t4);
-    mul(t4, t4, t3);
-    sqr(t4, t4);
-    mul(t4, t4, x);
-    sqr(t5, t4);
+    for (int i = 1; i < 13; i++) sqr_w(t4, t4);
+    mul_w(t4, t4, t3);
+    sqr_w(t4, t4);
+    mul_w(t4, t4, x);
+    sqr_w(t5, t4);
     MAB_NOUNROLL
-    for (int i = 1; i < 27; i++) sqr(t5, t5);
-    mul(t5, t5, t4);
-    sqr(t5, t5);
-    mul(t5, t5, x);
-    sqr(t4, t5);
+    for (int i = 1; i < 27; i++) sqr_w(t5, t5);
+    mul_w(t5, t5, t4);
+    sqr_w(t5, t5);
+    mul_w(t5, t5, x);
+    sqr_w(t4, t5);
     MAB_NOUNROLL
-    for (int i = 1; i < 55; i++) sqr(t4, t4);
-    mul(t4, t4, t5);
-    sqr(t4, t4);
-    mul(t4, t4, x);
-    sqr(t5, t4);
+    for (int i = 1; i < 55; i++) sqr_w(t4, t4);
+    mul_w(t4, t4, t5);
+    sqr_w(t4, t4);
+    mul_w(t4, t4, x);
+    sqr_w(t5, t4);
     MAB_NOUNROLL
-    for (int i = 1; i < 111; i++) sqr(t5, t5);
-    mul(t5, t5, t4);
-    sqr(t5, t5);
-    mul(t5, t5, x);
-    sqr(z, t5);
+    for (int i = 1; i < 111; i++) sqr_w(t5, t5);
+    mul_w(t5, t5, t4);
+    sqr_w(t5, t5);
+    mul_w(t5, t5, x);
+    sqr_w(z, t5);
     MAB_NOUNROLL
-    for (int i = 1; i < 14; i++) sqr(z, z);
-    mul(z, z, t3);
-    sqr(z, z);
+    for (int i = 1; i < 14; i++) sqr_w(z, z);
+    mul_w(z, z, t3);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 6; i++) sqr(z, z);
-    mul(z, z, t2);
-    sqr(z, z);
+    for (int i = 1; i < 6; i++) sqr_w(z, z);
+    mul_w(z, z, t2);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t1);
-    sqr(z, z);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t1);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 5; i++) sqr(z, z);
-    mul(z, z, x);
-    sqr(z, z);
+    for (int i = 1; i < 5; i++) sqr_w(z, z);
+    mul_w(z, z, x);
+    sqr_w(z, z);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(z, z);
-    mul(z, z, t0);
+    for (int i = 1; i < 3; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    if (WEAK) (void)canon(z, z);
   }
 };

@@ -1315,6 +1315,11 @@ struct F_X25519 {
 #endif
   }
 
+  // no separate weakly-reduced products in this plan: chains use the ordinary ones
+  static constexpr bool WEAK = false;
+  static MAB_DEV void mul_w(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { mul(r, a, b); }
+  static MAB_DEV void sqr_w(uint32_t (&r)[8], const uint32_t (&a)[8]) { sqr(r, a); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[8], const uint32_t (&b)[8]) {
 #ifndef MAB_HOSTSIM
@@ -1590,44 +1595,45 @@ struct F_X25519 {
     for (int i = 0; i < L; i++) x[i] = w[i];
     uint32_t t0[L];
     uint32_t t1[L];
-    sqr(t0, x);
-    mul(t0, t0, x);
-    sqr(t0, t0);
-    mul(t0, t0, x);
-    sqr(t1, t0);
+    sqr_w(t0, x);
+    mul_w(t0, t0, x);
+    sqr_w(t0, t0);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, x);
-    sqr(t0, t1);
+    for (int i = 1; i < 3; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, x);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 7; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(t0, t0);
-    mul(t0, t0, x);
-    sqr(t1, t0);
+    for (int i = 1; i < 7; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(t0, t0);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 15; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, x);
-    sqr(t0, t1);
+    for (int i = 1; i < 15; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, x);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 31; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(t1, t0);
+    for (int i = 1; i < 31; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 62; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, x);
-    sqr(t0, t1);
+    for (int i = 1; i < 62; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, x);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 125; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(z, t0);
-    sqr(z, z);
-    mul(z, z, x);
+    for (int i = 1; i < 125; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(z, t0);
+    sqr_w(z, z);
+    mul_w(z, z, x);
+    if (WEAK) (void)canon(z, z);
   }
 };

@@ -2517,6 +2517,11 @@ struct F_X448 {
   static MAB_DEV void add_tt(uint32_t (&r)[14], const uint32_t (&a)[14], const uint32_t (&b)[14]) { add(r, a, b); }
   static MAB_DEV void sub_tt(uint32_t (&r)[14], const uint32_t (&a)[14], const uint32_t (&b)[14]) { sub(r, a, b); }
 
+  // no separate weakly-reduced products in this plan: chains use the ordinary ones
+  static constexpr bool WEAK = false;
+  static MAB_DEV void mul_w(uint32_t (&r)[14], const uint32_t (&a)[14], const uint32_t (&b)[14]) { mul(r, a, b); }
+  static MAB_DEV void sqr_w(uint32_t (&r)[14], const uint32_t (&a)[14]) { sqr(r, a); }
+
   // n = -b (pseudo.py:329-348)
   static MAB_DEV void neg(uint32_t (&r)[14], const uint32_t (&b)[14]) {
 #ifndef MAB_HOSTSIM
@@ -2858,47 +2863,48 @@ struct F_X448 {
     for (int i = 0; i < L; i++) x[i] = w[i];
     uint32_t t0[L];
     uint32_t t1[L];
-    sqr(t0, x);
-    mul(t0, t0, x);
-    sqr(t0, t0);
-    mul(t0, t0, x);
-    sqr(t1, t0);
+    sqr_w(t0, x);
+    mul_w(t0, t0, x);
+    sqr_w(t0, t0);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 3; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t0, t1);
+    for (int i = 1; i < 3; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 6; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(t0, t0);
-    mul(t0, t0, x);
-    sqr(t1, t0);
+    for (int i = 1; i < 6; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(t0, t0);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 13; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, x);
-    sqr(t0, t1);
+    for (int i = 1; i < 13; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, x);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 27; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(t0, t0);
-    mul(t0, t0, x);
-    sqr(t1, t0);
+    for (int i = 1; i < 27; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(t0, t0);
+    mul_w(t0, t0, x);
+    sqr_w(t1, t0);
     MAB_NOUNROLL
-    for (int i = 1; i < 55; i++) sqr(t1, t1);
-    mul(t1, t1, t0);
-    sqr(t1, t1);
-    mul(t1, t1, x);
-    sqr(t0, t1);
+    for (int i = 1; i < 55; i++) sqr_w(t1, t1);
+    mul_w(t1, t1, t0);
+    sqr_w(t1, t1);
+    mul_w(t1, t1, x);
+    sqr_w(t0, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 111; i++) sqr(t0, t0);
-    mul(t0, t0, t1);
-    sqr(t1, t0);
-    mul(t1, t1, x);
-    sqr(z, t1);
+    for (int i = 1; i < 111; i++) sqr_w(t0, t0);
+    mul_w(t0, t0, t1);
+    sqr_w(t1, t0);
+    mul_w(t1, t1, x);
+    sqr_w(z, t1);
     MAB_NOUNROLL
-    for (int i = 1; i < 223; i++) sqr(z, z);
-    mul(z, z, t0);
+    for (int i = 1; i < 223; i++) sqr_w(z, z);
+    mul_w(z, z, t0);
+    if (WEAK) (void)canon(z, z);
   }
 };

@@ -30,7 +30,8 @@ template <class F> struct Field {
   }
   static MAB_DEV void nsqr(uint32_t (&a)[L], int n) {                          // modnsqr, pseudo.py:745-755
     MAB_NOUNROLL
-    for (int i = 0; i < n; i++) F::sqr(a, a);
+    for (int i = 0; i < n; i++) F::sqr_w(a, a);      // weakly reduced inside the chain where the plan has such a form
+    if (F::WEAK) (void)F::canon(a, a);
   }
   // modfsb, pseudo.py:272-283: canonicalise in place, return 1 iff the stored value was < p
   static MAB_DEV uint32_t fsb(uint32_t (&a)[L]) { return F::canon(a, a); }

@@ -63,7 +63,8 @@ template <class F, int OP> __global__ void __launch_bounds__(128) k_field(MabArg
   if constexpr (OP == OP_MULCHAIN) {        // measurement helper: r = a * b^scalar, register resident
     Fd::cpy(r, a);
     MAB_NOUNROLL
-    for (uint32_t it = 0; it < p.scalar; it++) F::mul(r, r, b);
+    for (uint32_t it = 0; it < p.scalar; it++) F::mul_w(r, r, b);
+    if (F::WEAK) (void)F::canon(r, r);
   }
   if constexpr (OP == OP_MLI) F::mli(r, a, p.scalar);
   if constexpr (OP == OP_CPY) Fd::cpy(r, a);
@@ -322,26 +323,57 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
   uint32_t* st = mab_smem + threadIdx.x;                               // K slots x 3 elements x L words
   uint32_t* stash = F::LADDER_STASH ? (mab_smem + MAB_LADDER_KMAX * 3 * L * T + threadIdx.x) : nullptr;
   const unsigned lane = threadIdx.x & 31;
-  unsigned home = 0;
-  if (Q.nq > 1) {
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    while (smid >= Q.sms) smid -= Q.sms;            // sparse SM numbering: fold (any mapping is correct)
-    home = smid * 4 + ((threadIdx.x >> 5) & 3);
-  }
-  unsigned q = home, visited = 0;
+  // The only scheduling state that lives across a ladder is `swept`: AT_HOME while the warp serves the queue of
+  // its own sub-partition, afterwards the number of queues behind the home queue already seen empty (counters
+  // only grow, so they stay empty).  The other queues are gone through 32 at a time, every lane peeking at one
+  // counter: a sweep over all SMs x 4 queues is a handful of round trips (a lane-0-only scan at the end of the
+  // kernel cost 7 % of a 2^17-key batch).
+  constexpr unsigned AT_HOME = 0xffffffffu;
+  unsigned swept = AT_HOME;
   for (;;) {
-    // next chunk: from the current queue, else move on to the next queue (each queue is left for good once
-    // it is seen empty: its counter only grows)
+    unsigned home = 0;
+    if (Q.nq > 1) {
+      unsigned smid;
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      while (smid >= Q.sms) smid -= Q.sms;            // sparse SM numbering: fold (any mapping is correct)
+      home = smid * 4 + ((threadIdx.x >> 5) & 3);
+    }
     int K = 0;
     unsigned first = 0;
     unsigned long long glo = 0;
-    while (visited < Q.nq) {
+    for (;;) {
+      unsigned q = home;
+      if (swept != AT_HOME) {
+        // the next queue behind home + swept that still holds chunks
+        bool found = false;
+        while (swept + 1 < Q.nq) {
+          const unsigned cand = swept + 1 + lane;                       // offset from home, 1 .. nq-1
+          int has = 0;
+          if (cand < Q.nq) {
+            unsigned qq = home + cand;
+            if (qq >= Q.nq) qq -= Q.nq;
+            unsigned long long lo2; unsigned g2, lg2;
+            mab_queue_range(Q, qq, lo2, g2, lg2);
+            const unsigned c4 = lg2 ? Q.c4l : Q.c4s, c2 = lg2 ? Q.c2l : Q.c2s;
+            has = *(volatile unsigned long long*)(Q.counter + qq) < (unsigned long long)(c4 + c2 + (g2 - 4 * c4 - 2 * c2));
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, has);
+          if (m) {
+            swept += (unsigned)(__ffs((int)m) - 1);                     // everything before it is empty for good
+            q = home + swept + 1;
+            if (q >= Q.nq) q -= Q.nq;
+            found = true;
+            break;
+          }
+          swept += 32;
+        }
+        if (!found) break;
+      }
       unsigned g, longer;
       mab_queue_range(Q, q, glo, g, longer);
-      unsigned long long ci = 0;
       const unsigned c4 = longer ? Q.c4l : Q.c4s, c2 = longer ? Q.c2l : Q.c2s;
       const unsigned nchunks = c4 + c2 + (g - 4 * c4 - 2 * c2);
+      unsigned long long ci = 0;
       int ok = 0;
       if (lane == 0) {
         // a plain read first: an exhausted queue costs a load, not an atomic
@@ -356,8 +388,9 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
         K = mab_queue_chunk(g, c4, c2, ci, first);
         if (K) break;
       }
-      q = (q + 1 == Q.nq) ? 0 : q + 1;
-      visited++;
+      // this queue is empty: the home queue is left for good; a stolen-from queue is swept past
+      swept = (swept == AT_HOME) ? 0 : swept + 1;
+      if (Q.nq == 1) break;
     }
     if (!K) break;
     const size_t start = (size_t)(glo + first) * 32;

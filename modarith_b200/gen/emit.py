@@ -55,7 +55,9 @@ def emit_field_header(plan: Plan) -> str:
     out.append("// plan %s: %d saturated 32-bit limbs; stored values < %s; R = 2^%d\n" % (
         type(plan).__name__, L, "p" if plan.bound == P.p else "2^%d" % (32 * L),
         plan.R.bit_length() - 1))
-    for k in ("mul", "sqr", "mli", "mla", "add", "sub", "canon") + (("add_tt", "sub_tt") if plan.tight else ()):
+    weak = "mul_w" in blocks
+    for k in ("mul", "sqr", "mli", "mla", "add", "sub", "canon") + (("add_tt", "sub_tt") if plan.tight else ()) + \
+            (("mul_w", "sqr_w") if weak else ()):
         w, i, a = blocks[k].stats()
         out.append("//   %-5s : %3d IMAD.WIDE  %2d IMAD  ~%3d ALU-pipe ops\n" % (k, w, i, a))
     out.append("//   modpro: %d squarings + %d multiplies (exponent (p-1-2^k)/2^(k+1), k=%d)\n" %
@@ -116,6 +118,18 @@ def emit_field_header(plan: Plan) -> str:
         out.append("  static constexpr bool TIGHT = false;\n")
         out.append("  static MAB_DEV void add_tt(%s, %s, %s) { add(r, a, b); }\n" % (r, a, b))
         out.append("  static MAB_DEV void sub_tt(%s, %s, %s) { sub(r, a, b); }\n\n" % (r, a, b))
+    if weak:
+        out.append("  // Weakly reduced products for chains (modpro, modnsqr): operands and results are any representative\n"
+                   "  // below 2^%d; the last step looks at the carry word only.  A chain ends with canon(), which restores\n"
+                   "  // the [0, p) invariant that every other function of this field keeps.\n" % (32 * L))
+        out.append("  static constexpr bool WEAK = true;\n")
+        out.append(_block_fn(plan, "mul_w", blocks["mul_w"], "%s, %s, %s" % (r, a, b)))
+        out.append(_block_fn(plan, "sqr_w", blocks["sqr_w"], "%s, %s" % (r, a)))
+    else:
+        out.append("  // no separate weakly-reduced products in this plan: chains use the ordinary ones\n")
+        out.append("  static constexpr bool WEAK = false;\n")
+        out.append("  static MAB_DEV void mul_w(%s, %s, %s) { mul(r, a, b); }\n" % (r, a, b))
+        out.append("  static MAB_DEV void sqr_w(%s, %s) { sqr(r, a); }\n\n" % (r, a))
     out.append("  // n = -b (pseudo.py:329-348)\n")
     out.append(_block_fn(plan, "neg", blocks["neg"], "%s, %s" % (r, b)))
     out.append("  // canonical residue of a stored value; returns 1 iff it was already < p\n"
@@ -155,17 +169,18 @@ def emit_field_header(plan: Plan) -> str:
         out.append("    uint32_t %s[L];\n" % t)
     for op in prog:
         if op[0] == "mul":
-            out.append("    mul(%s, %s, %s);\n" % (op[1], op[2], op[3]))
+            out.append("    mul_w(%s, %s, %s);\n" % (op[1], op[2], op[3]))
         else:
             dst, src, n = op[1], op[2], op[3]
             if n == 0:
                 out.append("    for (int i = 0; i < L; i++) %s[i] = %s[i];\n" % (dst, src))
             else:
-                out.append("    sqr(%s, %s);\n" % (dst, src))
+                out.append("    sqr_w(%s, %s);\n" % (dst, src))
                 if n == 2:
-                    out.append("    sqr(%s, %s);\n" % (dst, dst))
+                    out.append("    sqr_w(%s, %s);\n" % (dst, dst))
                 elif n > 2:
-                    out.append("    MAB_NOUNROLL\n    for (int i = 1; i < %d; i++) sqr(%s, %s);\n" % (n, dst, dst))
+                    out.append("    MAB_NOUNROLL\n    for (int i = 1; i < %d; i++) sqr_w(%s, %s);\n" % (n, dst, dst))
+    out.append("    if (WEAK) (void)canon(z, z);\n")
     out.append("  }\n")
     out.append("};\n")
     return "".join(out)

@@ -87,6 +87,9 @@ class Plan:
         if self.tight:
             self.blocks["add_tt"] = self.build_add_tt()
             self.blocks["sub_tt"] = self.build_sub_tt()
+        if getattr(self, "weak_bound", None):
+            self.blocks["mul_w"] = self.build_mul_w()
+            self.blocks["sqr_w"] = self.build_sqr_w()
         return self.blocks
 
     def _io(self, asm, ins, out="r"):
@@ -225,6 +228,18 @@ class Plan:
                 assert r < B and r % p == (x - y) % p, ("sub", hex(x), hex(y))
                 r, _ = self.run("mla", a=ax, c=ay, b=M32 >> 1)
                 assert r < B and r % p == (x * (M32 >> 1) + y) % p, ("mla", hex(x), hex(y))
+        if "mul_w" in self.blocks:
+            Wb = self.weak_bound
+            wedge = [0, 1, p - 1, p, p + 1, Wb - 1, Wb - 2, Wb >> 1, (Wb >> 1) + 1, Wb - (1 << 32), Wb - (1 << 224)]
+            ws = [v for v in wedge if 0 <= v < Wb]
+            pairs = [(a, b) for a in ws for b in ws] + [(rng.randrange(Wb), rng.randrange(Wb)) for _ in range(trials)]
+            for x, y in pairs:
+                r, _ = self.run("mul_w", a=words(x, L), b=words(y, L))
+                assert r < Wb and r % p == x * y * Rinv % p, ("mul_w", hex(x), hex(y))
+                r, _ = self.run("sqr_w", a=words(x, L))
+                assert r < Wb and r % p == x * x * Rinv % p, ("sqr_w", hex(x))
+                r2, _ = self.run("canon", a=words(r, L))
+                assert r2 == x * x * Rinv % p, ("canon after sqr_w", hex(x))
         if self.tight:
             # mul/sqr land below the tight bound for ANY stored operands; add_tt/sub_tt are exact on tight operands
             T = self.tight
@@ -793,6 +808,15 @@ class Montgomery(Plan):
         self.dinv_terms = _naf_terms(self.dinv, 32 * L)
         assert len(self.d_terms) <= 8 and len(self.dinv_terms) <= 8, "modulus is not shaped"
         self.R2 = self.R * self.R % prime.p           # nres constant (cw, monty.py:2246-2248)
+        # p + 1 = 2^g_shift * g, g a short signed sum of powers of two (see _redc)
+        g, sh = prime.p + 1, 0
+        while g % (1 << 32) == 0:
+            g >>= 32
+            sh += 32
+        assert sh >= 32, "p + 1 has no whole zero word at the bottom"
+        self.g_shift, self.g_terms = sh, _naf_terms(g, 32 * L)
+        assert len(self.g_terms) <= 8 and all(k % 32 == 0 for k, _ in self.g_terms)
+        self.weak_bound = self.R                      # mul_w / sqr_w: operands and results below R
 
     def _shifted(self, asm, src, k, N):
         """Words of (src << k) inside an N-word window: {index: reg}."""
@@ -840,17 +864,53 @@ class Montgomery(Plan):
             acc = acc[:lo] + new
         return acc
 
-    def _redc(self, asm, T):
-        """T: 2L words (< p*R) -> L words in [0,p)."""
+    def _redc(self, asm, T, weak=False):
+        """T: 2L words -> L words: (T + Q*p) / R with Q = T_lo * (-p^-1) mod R.
+
+        p + 1 = 2^s * g with g a short signed sum of powers of two (P-256: s = 96, g = 2^160 - 2^128 + 2^96 + 1),
+        so (T + Q*p) / R = (T - Q + 2^s * Q*g) / R: H = Q*g is built with three add/sub chains that stop at the
+        top of H (13 words), and ONE chain adds it to T from word s/32 upwards; the low L words of that sum equal Q
+        by construction, so `- Q` needs no instruction at all.  51 add/sub-with-carry instructions for P-256 where
+        the first formulation (U = Q*d over a 2L-word window, T_hi + Q - U_hi) took 60.
+        weak=False: operands < p, result < 2p, conditional subtraction -> [0, p).
+        weak=True : operands < R, result < R + p, p subtracted iff the carry word is set -> [0, R)."""
         L = self.L
-        lo, hi = T[:L], T[L:]
+        lo = T[:L]
         Q = self._signed_sum(asm, lo, self.dinv_terms, L, wrap_ok=True)
-        U = self._signed_sum(asm, Q, self.d_terms, 2 * L, wrap_ok=False)
-        m = asm.tmp(L + 1)
-        asm.add_chain(m[:L], hi, Q, carry_to=(m[L], 0))
-        n = asm.tmp(L + 1)
-        asm.sub_chain(n, m, U[L:] + [0])
-        return self._cond_sub_p9(asm, n)
+        sw = self.g_shift // 32
+        # Q*g < 2^(32(2L-sw)) fits; the positive terms alone can exceed it by a bit for Q within 2^-64 of R, so the
+        # chains work modulo 2^(32(2L-sw)) and the subtraction brings the value back
+        H = self._signed_sum(asm, Q, self.g_terms, 2 * L - sw, wrap_ok=True)
+        n = asm.tmp(2 * L - sw)
+        top = asm.tmp()
+        asm.add_chain(n, T[sw:], H, carry_to=(top, 0))
+        hi = n[L - sw:] + [top]
+        return self._weak_sub_p(asm, hi) if weak else self._cond_sub_p9(asm, hi)
+
+    def _weak_sub_p(self, asm, v):
+        """v: L+1 words, top word 0 or 1, value < R + p  ->  L words < R: subtract p iff the top word is set,
+        i.e. add d = R - p under a mask and drop the carry."""
+        L = self.L
+        dw = words(self.d, L)
+        m = asm.tmp()
+        asm.sub(m, 0, v[L])                                  # all-ones iff top set
+        asm.nocheck.add(len(asm.ins) - 1)
+        ops = []
+        for k in range(L):
+            if dw[k] == 0:
+                ops.append(0)
+            elif dw[k] == M32:
+                ops.append(m)
+            elif dw[k] == 1:
+                ops.append(v[L])
+            else:
+                t = asm.tmp()
+                asm.logic("and", t, m, dw[k])
+                ops.append(t)
+        r = asm.tmp(L)
+        asm.add_chain(r, v[:L], ops, wrap_ok=True)
+        # the chain's carry-out cancels the top word; the interpreter cannot see that, the bignum self-check does
+        return r
 
     def _cond_sub_p9(self, asm, v):
         """v: L+1 words, < 2p  ->  L words in [0,p)."""
@@ -870,6 +930,24 @@ class Montgomery(Plan):
 
     def reduce_wide(self, asm, T):
         return self._redc(asm, T)
+
+    # Weakly reduced products for chains of multiplications (modpro, modnsqr): operands and results are any
+    # representative below R = 2^(32L) (< 2p), and the final step looks at the carry word only -- 10 instructions
+    # where the full conditional subtraction takes 18.  A chain ends with `canon`, which brings the value back
+    # into [0, p), the invariant every other function of this plan keeps.
+    def build_mul_w(self):
+        asm = Asm(self.name + ".mul_w")
+        a, b = self._io(asm, ["a", "b"])
+        T = satmul.product(asm, a, b, link=self.link_products)
+        self._outs(asm, self._redc(asm, T, weak=True))
+        return asm
+
+    def build_sqr_w(self):
+        asm = Asm(self.name + ".sqr_w")
+        (a,) = self._io(asm, ["a"])
+        T = satmul.square(asm, a, link=self.link_products)
+        self._outs(asm, self._redc(asm, T, weak=True))
+        return asm
 
     def reduce_small(self, asm, T):
         """L+1 words (a*b, b < 2^32; no R factor involved, monty.py:876-978) -> [0,p):

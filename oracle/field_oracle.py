@@ -23,16 +23,15 @@ from __future__ import annotations
 import os
 import sys
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime  # noqa: E402  (data tables only)
-from modarith_b200 import addchain as _ac  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle_primes import TABLE as PRIMES, OraclePrime as Prime, lookup as _lookup  # noqa: E402  (the oracle's own tables)
 
 
 class FieldOracle:
     """Value-level model of the 32-function generated API for one modulus."""
 
     def __init__(self, prime: Prime | str):
-        self.P = PRIMES[prime] if isinstance(prime, str) else prime
+        self.P = _lookup(prime)
         self.p = self.P.p
         self.nbytes = self.P.nbytes
         self.k = self.P.pm1d2
@@ -91,9 +90,16 @@ class FieldOracle:
         return a
 
     def modpro(self, w):
-        """pseudo.py:758-785: progenitor w^PE, PE=(p-1-2^k)/2^(k+1) (pseudo.py:1574-1581),
-        evaluated by the same straight-line sqr/mul program shape (our own chain)."""
-        return _ac.evaluate(_ac.find_chain(self.pe), w, self.p)
+        """pseudo.py:758-785: progenitor w^PE, PE=(p-1-2^k)/2^(k+1) (pseudo.py:1574-1581).  The reference runs a
+        straight-line sqr/mul program read from addchain's output; the chain only fixes the ORDER of the squarings
+        and multiplications, never the value, so the oracle uses its own left-to-right square-and-multiply over
+        modsqr / modmul (nothing of the product's chain finder is used here)."""
+        r = 1
+        for bit in bin(self.pe)[2:] if self.pe else "":
+            r = self.modsqr(r)
+            if bit == "1":
+                r = self.modmul(r, w % self.p)
+        return r % self.p
 
     def modinv(self, x, h=None):
         """pseudo.py:788-812 / monty.py:1225-1251.  0 -> 0."""

@@ -1,5 +1,6 @@
 """Pin the oracle (oracle/field_oracle.py) before trusting it: every golden vector, known-answer
 test and fixture the reference holds for this path."""
+import os
 import random
 
 import numpy as np
@@ -258,3 +259,30 @@ def test_c_oracle_against_reference_build(ref_libs):
         n = 512 if c == "X25519" else 128
         k, u = util.random_bytes(71, n, nb), util.random_bytes(72, n, nb)
         assert np.array_equal(c_oracle.rfc7748_batch(c, k, u), util.ref_rfc7748_batch(ref_libs[c], k, u))
+
+
+def test_oracle_tables_are_its_own_and_agree_with_the_product():
+    """The oracle carries its own moduli and curve constants (oracle/oracle_primes.py, restated from the reference's
+    tables) and its own modpro; nothing under oracle/ imports the product package.  The two tables must agree."""
+    import re
+    import oracle_primes
+    from modarith_b200.primes import ALL_PRIMES
+    assert set(oracle_primes.TABLE) == set(ALL_PRIMES)
+    for name, P in ALL_PRIMES.items():
+        Q = oracle_primes.TABLE[name]
+        for key in ("p", "nbits", "nbytes", "pm1d2", "pe", "roi", "a24", "cof", "generator", "ed_d", "ed_gx", "ed_gy",
+                    "ed_order", "wb", "wgx", "wgy", "worder"):
+            assert getattr(Q, key) == getattr(P, key), (name, key)
+    root = os.path.join(os.path.dirname(__file__), "..", "oracle")
+    for fn in os.listdir(root):
+        # addchain_standin.py is not part of the checker: it feeds the REFERENCE generators an addition chain when
+        # oracle/_ref is built (the order of squarings / multiplications inside the reference's modpro, never a value)
+        # and deliberately hands them the chain the product uses, so that the CPU baseline is not slowed by a worse one
+        if fn.endswith(".py") and fn != "addchain_standin.py":
+            src = open(os.path.join(root, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+modarith_b200", src, re.M), fn
+    # modpro by the oracle's own square-and-multiply equals the plain power for every modulus
+    for name in ALL_PRIMES:
+        O = FieldOracle(name)
+        for w in (0, 1, 2, 3, O.p - 1, 0x123456789ABCDEF % O.p):
+            assert O.modpro(w) == pow(w, O.pe, O.p)

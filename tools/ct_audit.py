@@ -42,7 +42,7 @@ LOADS = ("LDG", "LDS", "LDL", "LD.", "LDSM")
 CLEAN_DEST = ("LDC", "LDCU", "ULDC", "S2R", "S2UR", "CS2R", "ATOM", "ATOMG", "ATOMS", "MOV32I")
 NO_DEST = ("ST", "RED", "BRA", "EXIT", "BAR", "BSYNC", "BSSY", "NOP", "WARPSYNC", "MEMBAR", "ERRBAR", "YIELD", "RET",
            "CALL", "DEPBAR", "ENDCOLLECTIVE", "CCTL", "NANOSLEEP", "BREAK", "KILL", "BPT", "JMP", "BRX", "JMX")
-TWO_PRED_DEST = ("ISETP", "UISETP", "PLOP3", "UPLOP3", "FSETP", "VOTE", "VOTEU", "ISETP.", "PSETP")
+TWO_PRED_DEST = ("ISETP", "UISETP", "PLOP3", "UPLOP3", "FSETP", "PSETP")
 VARIABLE_TIME = ("IDIV", "MUFU")          # value-dependent latency would be a leak; neither appears in the field code
 REG = re.compile(r"\b(UR\d+|UP\d+|R\d+|P\d+)\b")
 
