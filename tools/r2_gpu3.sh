@@ -14,3 +14,6 @@ print('lg',$LG,'single_queue',$Q,'value %.2f M/s  e2e %.2f M/s  frac %.4f parity
   done
 done
 timeout 600 python bench.py > gpurun_out/r2_bench2.json 2> gpurun_out/r2_bench2.err; tail -3 gpurun_out/r2_bench2.err; head -c 300 gpurun_out/r2_bench2.json
+# X448 at 3 CTAs/SM (168 registers, small spill) against the shipped 2 CTAs/SM build
+timeout 300 python tools/compare_kernels.py 2>&1 | grep X448 | sed 's/^/shipped  /' | tee gpurun_out/r2_x448_variants.txt
+MODARITH_B200_LIB=modarith_b200/build/variants/x448_mb3/libmodarith_b200.so timeout 300 python tools/compare_kernels.py 2>&1 | grep X448 | sed 's/^/mb3      /' | tee -a gpurun_out/r2_x448_variants.txt
