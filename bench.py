@@ -322,6 +322,41 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
             del ua, ub, uc
         out[name] = res
         del x, y, r, xs, ys, rs
+    # a consumer-shaped sequence of field calls (the complete P-256 point addition of weierstrass.c:69-160: 12 modmul +
+    # 2 by the curve constant + 29 modadd/modsub) as ONE mab_NIST256_modprog launch against one launch per call
+    try:
+        F = Field("NIST256", dev)
+        m = 1 << 21
+        ops = [F.modimp(torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=dev, generator=gen))[0] for _ in range(7)]
+        X1_, Y1_, Z1_, X2_, Y2_, Z2_, B_, t0, t1, t2, t3, t4, X3, Y3, Z3 = range(15)
+        code = [("mul", t0, X1_, X2_), ("mul", t1, Y1_, Y2_), ("mul", t2, Z1_, Z2_), ("add", t3, X1_, Y1_), ("add", t4, X2_, Y2_),
+                ("mul", t3, t3, t4), ("add", t4, t0, t1), ("sub", t3, t3, t4), ("add", t4, Y1_, Z1_), ("add", X3, Y2_, Z2_),
+                ("mul", t4, t4, X3), ("add", X3, t1, t2), ("sub", t4, t4, X3), ("add", X3, X1_, Z1_), ("add", Y3, X2_, Z2_),
+                ("mul", X3, X3, Y3), ("add", Y3, t0, t2), ("sub", Y3, X3, Y3), ("mul", Z3, B_, t2), ("sub", X3, Y3, Z3),
+                ("add", Z3, X3, X3), ("add", X3, X3, Z3), ("sub", Z3, t1, X3), ("add", X3, t1, X3), ("mul", Y3, B_, Y3),
+                ("add", t1, t2, t2), ("add", t2, t1, t2), ("sub", Y3, Y3, t2), ("sub", Y3, Y3, t0), ("add", t1, Y3, Y3),
+                ("add", Y3, t1, Y3), ("add", t1, t0, t0), ("add", t0, t1, t0), ("sub", t0, t0, t2), ("mul", t1, t4, Y3),
+                ("mul", t2, t0, Y3), ("mul", Y3, X3, Z3), ("add", Y3, Y3, t2), ("mul", X3, t3, X3), ("sub", X3, X3, t1),
+                ("mul", Z3, t4, Z3), ("mul", t1, t3, t0), ("add", Z3, Z3, t1)]
+        outs = [F.alloc(m) for _ in range(3)]
+        t = _time(lambda: F.modprog(code, ops, [X3, Y3, Z3], outputs=outs), 3)
+        R = [F.alloc(m) for _ in range(15)]
+        for k in range(7):
+            R[k].copy_(ops[k])
+
+        def separately():
+            for op, d, a, b in code:
+                (F.modmul if op == "mul" else F.modadd if op == "add" else F.modsub)(R[a], R[b], R[d])
+        ts = _time(separately, 2)
+        nmul = sum(1 for c in code if c[0] == "mul")
+        out["nist256_modprog_point_addition"] = {
+            "workload": "complete P-256 point addition as a 43-instruction modprog program, 2^21 point pairs",
+            "value": m / t, "unit": "additions/s", "one_launch_per_call_value": m / ts, "speedup": ts / t,
+            "field_ops_per_s": m * len(code) / t, "imad_frac": (m / t * nmul * 64 / pk) if pk else None,
+            "hbm_bytes_per_addition": 10 * 32, "one_launch_per_call_hbm_bytes": len(code) * 96}
+        del ops, outs, R
+    except Exception as ex:
+        out["nist256_modprog_point_addition"] = {"error": str(ex)[:200]}
     # the generator's fall-back plan (any odd modulus: full Montgomery with real multiplies), SURVEY.md 8f row 2
     for name in ("SECP256K1", "NIST256ORDER"):
         try:
@@ -334,7 +369,8 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
             t = _time(lambda: F.bench_modmul(x, y, r, iters), 2)
             out[name] = {"modmul_register_resident": {"value": m * iters / t / 1e9, "unit": "Gop/s", "chain": iters,
                                                       "imad_frac": (m * iters / t * L * L / pk) if pk else None,
-                                                      "note": "MontgomeryFull plan: word-serial Montgomery, 2 L^2 wide multiplies + L plain ones per modmul"}}
+                                                      "note": ("PseudoMersenne33 plan: 2^256 == 2^32 + 977, L^2 + L + 1 wide multiplies per modmul" if name == "SECP256K1"
+                                                               else "MontgomeryFull plan: word-serial Montgomery, 2 L^2 wide multiplies + L plain ones per modmul")}}
             del x, y, r
         except Exception as ex:
             out[name] = {"error": str(ex)[:200]}

@@ -78,6 +78,41 @@ MAB_API int mab_pipe_probe(int variant, int iters, int blocks, int threads, floa
 MAB_API int mab_probe_unsat29_modmul(const uint32_t *a, const uint32_t *b, uint32_t *c, unsigned int iters,
                                      size_t n, size_t stride, void *stream);
 
+/* ---- straight-line programs of field operations (mab_<P>_modprog) ------------------------------ */
+/* What a consumer of the generated functions actually runs is a SEQUENCE of calls on a few variables (the
+ * complete point addition of weierstrass.c:69-160 is 14 modmul + 23 modadd/modsub on 10 spint arrays).  One
+ * launch per call moves 3 x 4 x Nlimbs bytes per element through HBM each time; mab_<P>_modprog executes the
+ * whole sequence in ONE launch with the variables held on chip.  A program is an array of mab_insn over
+ * MAB_PROG_NREG field registers: registers 0 .. nin-1 are loaded from the limb planes in[0..nin-1] before the
+ * first instruction, and register out_reg[k] is stored to the limb planes out[k] after the last (k < nout).
+ * Semantics of every operation = the generated function of the same name (same results as calling
+ * mab_<P>_mod<op> with the same operands); dst may equal a or b, as the reference allows aliasing.
+ * `code`, `in`, `out`, `out_reg` are HOST arrays (of device plane pointers); at most MAB_PROG_MAX instructions. */
+#define MAB_PROG_NREG 16
+#define MAB_PROG_MAX 320
+enum mab_opcode {
+  MAB_OP_ADD = 0, /* dst = a + b        modadd */
+  MAB_OP_SUB,     /* dst = a - b        modsub */
+  MAB_OP_NEG,     /* dst = -a           modneg */
+  MAB_OP_MUL,     /* dst = a * b        modmul */
+  MAB_OP_SQR,     /* dst = a^2          modsqr */
+  MAB_OP_MLI,     /* dst = a * imm      modmli, 0 <= imm < 2^31 */
+  MAB_OP_CPY,     /* dst = a            modcpy */
+  MAB_OP_NSQR,    /* dst = a^(2^imm)    modcpy + modnsqr */
+  MAB_OP_PRO,     /* dst = a^PE         modpro */
+  MAB_OP_INV,     /* dst = 1/a, 0 -> 0  modinv(a, NULL, dst) */
+  MAB_OP_SQRT,    /* dst = sqrt(a)      modsqrt(a, NULL, dst) */
+  MAB_OP_ZER,     /* dst = 0            modzer */
+  MAB_OP_ONE,     /* dst = 1            modone */
+  MAB_OP_INT,     /* dst = imm          modint */
+  MAB_OP_HAF,     /* dst = a / 2        modcpy + modhaf */
+  MAB_OP_COUNT
+};
+typedef struct mab_insn {
+  unsigned char op, dst, a, b; /* enum mab_opcode, then register numbers 0 .. MAB_PROG_NREG-1 */
+  uint32_t imm;                /* small-integer operand of MLI / NSQR / INT */
+} mab_insn;
+
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
   /* macros of the generated header (pseudo.py:1403-1407) plus the modpro chain cost; any pointer may be NULL */ \
@@ -138,7 +173,10 @@ MAB_API int mab_probe_unsat29_modmul(const uint32_t *a, const uint32_t *b, uint3
   MAB_API int mab_##P##_modimp(const char *b, uint32_t *a, int *status, size_t n, size_t stride, void *stream);   \
   /* modsign / modcmp  pseudo.py:1149-1174 */                                                             \
   MAB_API int mab_##P##_modsign(const uint32_t *a, int *out, size_t n, size_t stride, void *stream);              \
-  MAB_API int mab_##P##_modcmp(const uint32_t *a, const uint32_t *b, int *out, size_t n, size_t stride, void *stream);
+  MAB_API int mab_##P##_modcmp(const uint32_t *a, const uint32_t *b, int *out, size_t n, size_t stride, void *stream); \
+  /* a sequence of the calls above in one launch, see "straight-line programs" */                       \
+  MAB_API int mab_##P##_modprog(const mab_insn *code, size_t ncode, const uint32_t *const *in, int nin, uint32_t *const *out, \
+                                const unsigned char *out_reg, int nout, size_t n, size_t stride, void *stream);
 
 MAB_DECLARE_FIELD(X25519)
 MAB_DECLARE_FIELD(X448)

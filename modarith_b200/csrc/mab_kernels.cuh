@@ -8,6 +8,7 @@
 // the widest vector access the pointer alignment allows.
 #pragma once
 #include <cuda_runtime.h>
+#include "modarith_b200.h"
 #include "rfc7748_sm100.cuh"
 #include "weierstrass_sm100.cuh"
 #include "edwards_sm100.cuh"
@@ -151,6 +152,82 @@ template <class F, int K> __global__ void __launch_bounds__(128) k_inv_shared(Ma
     Fd::zer(zero);
     Fd::cmv((flags >> j) & 1u, zero, r);
     if (i < nn) plane_st<L>(p.r, p.stride, i, r);
+  }
+}
+
+// ---- modprog: a straight-line program of field operations in ONE launch ----------------------------
+// The reference's consumers are sequences of field calls on a handful of elements (the complete addition of
+// weierstrass.c:69-160 is 14 multiplications and 23 additions on 10 variables); one launch per call would move
+// 3 x 4L bytes per element through HBM for every one of them.  Here the variables of a program live on chip:
+// MAB_PROG_NREG field registers per thread in shared memory (column layout: word w of register r of thread t at
+// [(r*L + w)*128 + t], conflict-free), operands are read into machine registers, the generated arithmetic runs,
+// and the result goes back to shared memory.  The program is uniform across the batch (it arrives in kernel
+// parameter space, i.e. the constant bank), so there is no divergence and nothing data-dependent in control
+// flow or addressing.  Inputs are loaded from limb planes into registers 0 .. nin-1 before the first
+// instruction; any registers can be stored to limb planes after the last.
+#define MAB_PROG_NREG 16
+#define MAB_PROG_MAX 320
+#define MAB_PROG_THREADS 128
+struct MabProg {
+  const uint32_t* in[MAB_PROG_NREG];
+  uint32_t* out[MAB_PROG_NREG];
+  unsigned char out_reg[MAB_PROG_NREG];
+  int nin, nout, ncode;
+  size_t n, stride;
+  mab_insn code[MAB_PROG_MAX];
+};
+template <class F> __global__ void __launch_bounds__(MAB_PROG_THREADS) k_prog(const __grid_constant__ MabProg P) {
+  constexpr int L = F::L;
+  constexpr int T = MAB_PROG_THREADS;
+  typedef Field<F> Fd;
+  extern __shared__ uint32_t mab_smem[];
+  uint32_t* rf = mab_smem + threadIdx.x;
+  const size_t i = (size_t)blockIdx.x * T + threadIdx.x;
+  const bool live = i < P.n;
+  auto ld = [&](uint32_t (&x)[L], int r) {
+#pragma unroll
+    for (int w = 0; w < L; w++) x[w] = rf[(r * L + w) * T];
+  };
+  auto st = [&](int r, const uint32_t (&x)[L]) {
+#pragma unroll
+    for (int w = 0; w < L; w++) rf[(r * L + w) * T] = x[w];
+  };
+  for (int k = 0; k < P.nin; k++) {
+    uint32_t x[L];
+#pragma unroll
+    for (int w = 0; w < L; w++) x[w] = live ? P.in[k][w * P.stride + i] : 0u;
+    st(k, x);
+  }
+  MAB_NOUNROLL
+  for (int pc = 0; pc < P.ncode; pc++) {
+    const mab_insn I = P.code[pc];
+    uint32_t a[L], b[L], r[L];
+    switch (I.op) {
+      case MAB_OP_ADD: ld(a, I.a); ld(b, I.b); F::add(r, a, b); break;
+      case MAB_OP_SUB: ld(a, I.a); ld(b, I.b); F::sub(r, a, b); break;
+      case MAB_OP_MUL: ld(a, I.a); ld(b, I.b); F::mul(r, a, b); break;
+      case MAB_OP_NEG: ld(a, I.a); F::neg(r, a); break;
+      case MAB_OP_SQR: ld(a, I.a); F::sqr(r, a); break;
+      case MAB_OP_MLI: ld(a, I.a); F::mli(r, a, I.imm); break;
+      case MAB_OP_CPY: ld(r, I.a); break;
+      case MAB_OP_NSQR: ld(r, I.a); Fd::nsqr(r, (int)I.imm); break;
+      case MAB_OP_PRO: ld(a, I.a); F::pro(r, a); break;
+      case MAB_OP_INV: ld(a, I.a); Fd::template inv<false>(r, a, a); break;
+      case MAB_OP_SQRT: ld(a, I.a); Fd::template sqrt<false>(r, a, a); break;
+      case MAB_OP_ZER: Fd::zer(r); break;
+      case MAB_OP_ONE: Fd::one(r); break;
+      case MAB_OP_INT: Fd::from_int(r, I.imm); break;
+      case MAB_OP_HAF: ld(r, I.a); Fd::haf(r); break;
+      default: Fd::zer(r); break;
+    }
+    st(I.dst, r);
+  }
+  if (!live) return;
+  for (int k = 0; k < P.nout; k++) {
+    uint32_t x[L];
+    ld(x, P.out_reg[k]);
+#pragma unroll
+    for (int w = 0; w < L; w++) P.out[k][w * P.stride + i] = x[w];
   }
 }
 

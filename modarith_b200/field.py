@@ -212,6 +212,56 @@ class Field:
         self._call("modcmp", [_ptr(a), _ptr(b), _ptr(out)], self._chk(a, b))
         return out
 
+    # -- a sequence of the calls above in ONE launch (mab_<P>_modprog) ---------------------------
+    def modprog(self, code, inputs, out_regs, outputs=None):
+        """Run a straight-line program with its variables held on chip.
+
+        code     : [(op, dst, a, b)] or [(op, dst, a, b, imm)] with op one of add sub neg mul sqr mli cpy nsqr pro
+                   inv sqrt zer one int haf; dst / a / b are register numbers 0..15 (unused ones may be 0);
+                   semantics of each op = the API function of the same name
+        inputs   : limb-plane tensors, loaded into registers 0, 1, ... before the first instruction
+        out_regs : registers to store after the last instruction; returns one plane tensor per entry
+                   (written into `outputs` when given)
+        E.g. (x + y)^2 - x*y:  F.modprog([("add", 2, 0, 1), ("sqr", 2, 2, 0), ("mul", 3, 0, 1), ("sub", 2, 2, 3)], [x, y], [2])"""
+        import ctypes
+        if not code or len(code) > _lib.PROG_MAX:
+            raise ValueError("a program has 1 .. %d instructions" % _lib.PROG_MAX)
+        if len(inputs) > _lib.PROG_NREG or len(out_regs) > _lib.PROG_NREG or not out_regs:
+            raise ValueError("at most %d inputs and 1 .. %d outputs" % (_lib.PROG_NREG, _lib.PROG_NREG))
+        arr = (_lib.mab_insn * len(code))()
+        for k, ins in enumerate(code):
+            if len(ins) not in (4, 5) or ins[0] not in _lib.OPCODES:
+                raise ValueError("instruction %d: expected (op, dst, a, b[, imm]) with a known op, got %r" % (k, ins))
+            regs = ins[1:4]
+            if any((not isinstance(r, int)) or r < 0 or r >= _lib.PROG_NREG for r in regs):
+                raise ValueError("instruction %d: register numbers are 0 .. %d" % (k, _lib.PROG_NREG - 1))
+            imm = int(ins[4]) if len(ins) == 5 else 0
+            if imm < 0 or imm > 0x7FFFFFFF:
+                raise ValueError("instruction %d: the small-integer operand must be in [0, 2^31)" % k)
+            arr[k].op, arr[k].dst, arr[k].a, arr[k].b, arr[k].imm = _lib.OPCODES[ins[0]], regs[0], regs[1], regs[2], imm
+        if any((not isinstance(r, int)) or r < 0 or r >= _lib.PROG_NREG for r in out_regs):
+            raise ValueError("output registers are 0 .. %d" % (_lib.PROG_NREG - 1))
+        ref = self._chk(*inputs) if inputs else None
+        if outputs is None:
+            if ref is None:
+                raise ValueError("a program without inputs needs explicit output tensors (they define n)")
+            outputs = [torch.empty_like(ref) for _ in out_regs]
+        if len(outputs) != len(out_regs):
+            raise ValueError("one output tensor per output register")
+        ref = self._chk(*(list(inputs) + list(outputs)))
+        n, stride = ref.shape[1], ref.stride(0) if ref.shape[1] > 0 else 0
+        if ref.shape[1] > 1 and ref.stride(1) != 1:
+            raise ValueError("limb planes must be contiguous along the element axis")
+        ins_p = (ctypes.c_void_p * max(1, len(inputs)))(*[t.data_ptr() for t in inputs])
+        out_p = (ctypes.c_void_p * len(outputs))(*[t.data_ptr() for t in outputs])
+        regs_p = (ctypes.c_ubyte * len(out_regs))(*out_regs)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        name = "mab_%s_modprog" % self.prime
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(self.lib, name)(arr, len(code), ins_p, len(inputs), out_p, regs_p, len(outputs), n,
+                                               max(stride, n), stream), name)
+        return outputs
+
     # -- conveniences for tests / small batches ------------------------------------------------
     def from_ints(self, values):
         """Python integers (< 2^(8*Nbytes)) -> planes via modimp."""

@@ -58,6 +58,17 @@ FIELD_SIGNATURES = {
     "modcmp": [_P, _P, _P],
 }
 
+
+class mab_insn(ctypes.Structure):
+    """include/modarith_b200.h: one instruction of a mab_<P>_modprog program."""
+    _fields_ = [("op", ctypes.c_ubyte), ("dst", ctypes.c_ubyte), ("a", ctypes.c_ubyte), ("b", ctypes.c_ubyte),
+                ("imm", ctypes.c_uint32)]
+
+
+OPCODES = {n: i for i, n in enumerate(("add", "sub", "neg", "mul", "sqr", "mli", "cpy", "nsqr", "pro", "inv", "sqrt",
+                                       "zer", "one", "int", "haf"))}
+PROG_NREG, PROG_MAX = 16, 320
+
 _lib = None
 
 
@@ -90,6 +101,11 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, "mab_%s_%s" % (P, name))
             fn.argtypes = lead + ([] if name == "info" else _TAIL)
             fn.restype = c_int
+    for P in PRIMES:
+        fn = getattr(lib, "mab_%s_modprog" % P)
+        fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
+                       c_int, c_size_t, c_size_t, c_void_p]
+        fn.restype = c_int
     lib.mab_NIST256_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
     lib.mab_NIST256_ecnmul.restype = c_int
     lib.mab_ED25519_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
@@ -122,7 +138,7 @@ def exported_symbols():
             "mab_pipe_probe", "mab_release_workspaces", "mab_probe_unsat29_modmul",
             "mab_NIST256_ecnmul", "mab_ED25519_ecnmul", "mab_NIST256_ecnmul2", "mab_ED25519_ecnmul2"]
     for P in PRIMES:
-        syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES]
+        syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES] + ["mab_%s_modprog" % P]
     for P in CURVES:
         syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_validate" % P,
                  "mab_%s_rfc7748_perkey" % P, "mab_%s_rfc7748_host_multi" % P]

@@ -36,7 +36,8 @@ DEFAULT = [("mab_capi_X25519.o", "k_rfc7748"), ("mab_capi_X448.o", "k_rfc7748"),
            ("mab_capi_NIST256.o", "k_ecnmul"), ("mab_capi_X25519.o", "k_ecnmul"),
            ("mab_capi_NIST256.o", "k_field"), ("mab_capi_X25519.o", "k_field"), ("mab_capi_X448.o", "k_field"),
            ("mab_capi_SECP256K1.o", "k_field"), ("mab_capi_NIST256ORDER.o", "k_field"),
-           ("mab_capi_NIST256.o", "k_inv_shared"), ("mab_capi_X25519.o", "k_inv_shared")]
+           ("mab_capi_NIST256.o", "k_inv_shared"), ("mab_capi_X25519.o", "k_inv_shared"),
+           ("mab_capi_NIST256.o", "k_prog"), ("mab_capi_X25519.o", "k_prog"), ("mab_capi_X448.o", "k_prog")]
 
 LOADS = ("LDG", "LDS", "LDL", "LD.", "LDSM")
 CLEAN_DEST = ("LDC", "LDCU", "ULDC", "S2R", "S2UR", "CS2R", "ATOM", "ATOMG", "ATOMS", "MOV32I")
