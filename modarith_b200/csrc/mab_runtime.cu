@@ -237,6 +237,23 @@ const char* mab_error_string(int code) {
 
 void mab_release_workspaces(void) {
   {
+    std::lock_guard<std::mutex> g(g_counter_mutex);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < MAB_WS_MAXDEV; d++) {
+      if (!g_counters[d]) continue;
+      cudaSetDevice(d);
+      cudaDeviceSynchronize();                       // no kernel may still be drawing from the counters
+      for (int i = 0; i < MAB_NSLOTS; i++) cudaEventDestroy(g_slots[d][i].done);
+      delete[] g_slots[d];
+      g_slots[d] = nullptr;
+      cudaFree(g_counters[d]);
+      g_counters[d] = nullptr;
+      g_counter_next[d] = 0;
+    }
+    cudaSetDevice(prev);
+  }
+  {
     std::lock_guard<std::mutex> g(g_pool_mutex);
     for (int d = 0; d < MAB_WS_MAXDEV; d++)
       if (g_pool_ready[d]) {

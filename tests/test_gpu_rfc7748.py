@@ -256,3 +256,34 @@ def test_cross_check_openssl():
         except Exception:
             continue            # OpenSSL rejects all-zero shared secrets
         assert out[i].tobytes() == want
+
+
+def test_many_outstanding_launches_on_several_streams():
+    """More launches in flight than the library has work-counter slots (256), spread over several streams: a slot
+    is only handed out again after the launch that used it last has finished (event per slot)."""
+    from modarith_b200.rfc7748 import rfc7748
+    nb, n = 32, 2500
+    k, u = util.random_bytes(61, n, nb), util.random_bytes(62, n, nb)
+    want = _gpu("X25519", k, u)
+    dk, du = torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda()
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    outs = []
+    for i in range(300):
+        s = streams[i % 4]
+        with torch.cuda.stream(s):
+            outs.append(rfc7748("X25519", dk, du))
+    torch.cuda.synchronize()
+    for i in (0, 1, 2, 3, 150, 255, 256, 257, 299):
+        assert np.array_equal(outs[i].cpu().numpy(), want), i
+
+
+def test_release_workspaces_then_reuse():
+    from modarith_b200 import lib as mlib
+    from modarith_b200.rfc7748 import rfc7748
+    k, u = util.random_bytes(63, 777, 32), util.random_bytes(64, 777, 32)
+    want = _gpu("X25519", k, u)
+    assert np.array_equal(rfc7748("X25519", k, u), want)          # host route: creates the per-device workspace
+    torch.cuda.synchronize()
+    mlib.load().mab_release_workspaces()
+    assert np.array_equal(_gpu("X25519", k, u), want)
+    assert np.array_equal(rfc7748("X25519", k, u), want)
