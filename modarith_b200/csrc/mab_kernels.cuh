@@ -172,55 +172,93 @@ struct MabProg {
   const uint32_t* in[MAB_PROG_NREG];
   uint32_t* out[MAB_PROG_NREG];
   unsigned char out_reg[MAB_PROG_NREG];
-  int nin, nout, ncode;
+  int nin, nout, ncode, nreg;      // nreg: registers the program touches (sizes the shared-memory register file)
   size_t n, stride;
   mab_insn code[MAB_PROG_MAX];
 };
+// vector type of one shared-memory access of the register file: 16 bytes when L is a multiple of 4, else 8 or 4
+template <int L> struct MabProgVec { typedef uint32_t type; static constexpr int W = 1; };
+template <> struct MabProgVec<8> { typedef uint4 type; static constexpr int W = 4; };
+template <> struct MabProgVec<12> { typedef uint4 type; static constexpr int W = 4; };
+template <> struct MabProgVec<16> { typedef uint4 type; static constexpr int W = 4; };
+template <> struct MabProgVec<14> { typedef uint2 type; static constexpr int W = 2; };
+template <> struct MabProgVec<10> { typedef uint2 type; static constexpr int W = 2; };
+template <> struct MabProgVec<6> { typedef uint2 type; static constexpr int W = 2; };
+
 template <class F> __global__ void __launch_bounds__(MAB_PROG_THREADS) k_prog(const __grid_constant__ MabProg P) {
   constexpr int L = F::L;
   constexpr int T = MAB_PROG_THREADS;
   typedef Field<F> Fd;
-  extern __shared__ uint32_t mab_smem[];
-  uint32_t* rf = mab_smem + threadIdx.x;
+  typedef typename MabProgVec<L>::type V;
+  constexpr int VW = MabProgVec<L>::W, NV = L / VW;       // a register is NV vectors of VW words
+  static_assert(NV * VW == L, "vector width must divide the limb count");
+  // chunk c of register r of thread t at rf[(r*NV + c)*T + t]: consecutive threads, consecutive vectors -- every
+  // access of a warp is one conflict-free wavefront per 128 bytes
+  extern __shared__ uint4 mab_smem4[];
+  V* rf = reinterpret_cast<V*>(mab_smem4) + threadIdx.x;
   const size_t i = (size_t)blockIdx.x * T + threadIdx.x;
   const bool live = i < P.n;
   auto ld = [&](uint32_t (&x)[L], int r) {
 #pragma unroll
-    for (int w = 0; w < L; w++) x[w] = rf[(r * L + w) * T];
+    for (int c = 0; c < NV; c++) {
+      const V v = rf[(r * NV + c) * T];
+      const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int w = 0; w < VW; w++) x[c * VW + w] = pv[w];
+    }
   };
   auto st = [&](int r, const uint32_t (&x)[L]) {
 #pragma unroll
-    for (int w = 0; w < L; w++) rf[(r * L + w) * T] = x[w];
+    for (int c = 0; c < NV; c++) {
+      V v;
+      uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+      for (int w = 0; w < VW; w++) pv[w] = x[c * VW + w];
+      rf[(r * NV + c) * T] = v;
+    }
   };
-  for (int k = 0; k < P.nin; k++) {
+  // registers 0 .. nin-1 from the input planes, the others zero (a program that reads a register it never wrote
+  // sees 0, not what an earlier CTA left in shared memory)
+  for (int k = 0; k < P.nreg; k++) {
     uint32_t x[L];
 #pragma unroll
-    for (int w = 0; w < L; w++) x[w] = live ? P.in[k][w * P.stride + i] : 0u;
+    for (int w = 0; w < L; w++) x[w] = (live && k < P.nin) ? P.in[k][w * P.stride + i] : 0u;
     st(k, x);
   }
+  // the result of the previous instruction stays in machine registers and is forwarded to the next instruction's
+  // operands (chains like t = t*u; t = t - v read one operand less from shared memory); the choice is uniform
+  // across the batch, so it is a branch on the program, not on data
+  uint32_t r[L];
+  Fd::zer(r);
+  int last = -1;
   MAB_NOUNROLL
   for (int pc = 0; pc < P.ncode; pc++) {
     const mab_insn I = P.code[pc];
-    uint32_t a[L], b[L], r[L];
+    uint32_t a[L], b[L];
+    const bool two = (I.op == MAB_OP_ADD || I.op == MAB_OP_SUB || I.op == MAB_OP_MUL);
+    const bool one = !(I.op == MAB_OP_ZER || I.op == MAB_OP_ONE || I.op == MAB_OP_INT);
+    if (one) { if ((int)I.a == last) Fd::cpy(a, r); else ld(a, I.a); }
+    if (two) { if ((int)I.b == last) Fd::cpy(b, r); else ld(b, I.b); }
     switch (I.op) {
-      case MAB_OP_ADD: ld(a, I.a); ld(b, I.b); F::add(r, a, b); break;
-      case MAB_OP_SUB: ld(a, I.a); ld(b, I.b); F::sub(r, a, b); break;
-      case MAB_OP_MUL: ld(a, I.a); ld(b, I.b); F::mul(r, a, b); break;
-      case MAB_OP_NEG: ld(a, I.a); F::neg(r, a); break;
-      case MAB_OP_SQR: ld(a, I.a); F::sqr(r, a); break;
-      case MAB_OP_MLI: ld(a, I.a); F::mli(r, a, I.imm); break;
-      case MAB_OP_CPY: ld(r, I.a); break;
-      case MAB_OP_NSQR: ld(r, I.a); Fd::nsqr(r, (int)I.imm); break;
-      case MAB_OP_PRO: ld(a, I.a); F::pro(r, a); break;
-      case MAB_OP_INV: ld(a, I.a); Fd::template inv<false>(r, a, a); break;
-      case MAB_OP_SQRT: ld(a, I.a); Fd::template sqrt<false>(r, a, a); break;
+      case MAB_OP_ADD: F::add(r, a, b); break;
+      case MAB_OP_SUB: F::sub(r, a, b); break;
+      case MAB_OP_MUL: F::mul(r, a, b); break;
+      case MAB_OP_NEG: F::neg(r, a); break;
+      case MAB_OP_SQR: F::sqr(r, a); break;
+      case MAB_OP_MLI: F::mli(r, a, I.imm); break;
+      case MAB_OP_CPY: Fd::cpy(r, a); break;
+      case MAB_OP_NSQR: Fd::cpy(r, a); Fd::nsqr(r, (int)I.imm); break;
+      case MAB_OP_PRO: F::pro(r, a); break;
+      case MAB_OP_INV: Fd::template inv<false>(r, a, a); break;
+      case MAB_OP_SQRT: Fd::template sqrt<false>(r, a, a); break;
       case MAB_OP_ZER: Fd::zer(r); break;
       case MAB_OP_ONE: Fd::one(r); break;
       case MAB_OP_INT: Fd::from_int(r, I.imm); break;
-      case MAB_OP_HAF: ld(r, I.a); Fd::haf(r); break;
+      case MAB_OP_HAF: Fd::cpy(r, a); Fd::haf(r); break;
       default: Fd::zer(r); break;
     }
     st(I.dst, r);
+    last = I.dst;
   }
   if (!live) return;
   for (int k = 0; k < P.nout; k++) {

@@ -121,7 +121,7 @@ class Asm:
         return self._emit("prmt", d, (a, b, sel))
 
     # ---- carry-chain helpers -------------------------------------------
-    def wide_chain(self, slots, last_carry_to=None, first=True, carry_in=False):
+    def wide_chain(self, slots, last_carry_to=None, first=True, carry_in=False, keep_carry=False):
         """One carry chain of 32x32->64 multiply-accumulates.
 
         slots: list of (lo_dst, hi_dst, a, b, lo_addend, hi_addend); consecutive
@@ -133,7 +133,7 @@ class Asm:
         n = len(slots)
         for k, (lo, hi, a, b, clo, chi) in enumerate(slots):
             self.madlo(lo, a, b, clo, cin=(k > 0 or carry_in), cout=True)
-            last = (k == n - 1) and last_carry_to is None
+            last = (k == n - 1) and last_carry_to is None and not keep_carry      # keep_carry: the caller consumes CC
             self.madhi(hi, a, b, chi, cin=True, cout=not last)
         if last_carry_to is not None:
             d, c = last_carry_to

@@ -29,6 +29,11 @@ M32 = 0xFFFFFFFF
 # generator tuning knobs (kernel experiments; defaults are what measured best on B200)
 SMART_CAPTURE = os.environ.get("MAB_CAPTURE", "smart") == "smart"
 ZERO_REG = os.environ.get("MAB_ZERO", "lit") == "reg"
+# MAB_ROWS=fresh: within each accumulator array the row that opens a new top window is emitted BEFORE the row
+# whose chain carries into that window, and the carry is added onto the live window (two add-with-carry
+# instructions) instead of being captured in a word of its own that later needs a zero partner to form an
+# aligned (carry, 0) addend pair (ptxas materialises that zero with HFMA2 on the multiplier pipe half the time)
+ROW_ORDER = os.environ.get("MAB_ROWS", "natural")
 
 
 class _Acc:
@@ -84,9 +89,22 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords, carry_in=False):
         acc.ub[s + 1] = M32 if cin else (vmax >> 32)
     top = prods[-1][0] + 2
     if top < nwords and (cin or not SMART_CAPTURE):
-        c = acc.src(top)
-        asm.wide_chain(slots, last_carry_to=(acc.dst(top), c), carry_in=carry_in)
-        acc.ub[top] = min(M32, acc.ub[top] + 1)
+        if ROW_ORDER == "fresh" and top + 1 < nwords and acc.live[top] and acc.live[top + 1]:
+            # the window above is live: add the carry onto it; the window holds few enough products that it cannot
+            # overflow (bound tracked in ub, re-checked by the interpreter on concrete values)
+            vmax = ((acc.ub[top + 1] << 32) | acc.ub[top]) + 1
+            assert vmax >> 64 == 0, "carry into a live window could ripple further"
+            asm.wide_chain(slots, last_carry_to=None, carry_in=carry_in, keep_carry=True)
+            lo, hi = acc.reg[top], acc.reg[top + 1]
+            nlo, nhi = asm.tmp(), asm.tmp()
+            asm.add(nlo, lo, 0, cin=True, cout=True)
+            asm.add(nhi, hi, 0, cin=True, cout=False)
+            acc.reg[top], acc.reg[top + 1] = nlo, nhi
+            acc.ub[top], acc.ub[top + 1] = vmax & M32 if (vmax >> 32) == 0 else M32, min(M32, vmax >> 32)
+        else:
+            c = acc.src(top)
+            asm.wide_chain(slots, last_carry_to=(acc.dst(top), c), carry_in=carry_in)
+            acc.ub[top] = min(M32, acc.ub[top] + 1)
     else:
         asm.wide_chain(slots, last_carry_to=None, carry_in=carry_in)
 
@@ -120,11 +138,17 @@ def product_eo(asm: Asm, a, b):
     assert len(b) == L
     n = 2 * L
     E, O = _Acc(asm, n), _Acc(asm, n)
-    for i in range(L):
-        ev = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 0]
-        od = [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 1]
-        _row_chain(asm, E, ev, n)
-        _row_chain(asm, O, od, n)
+    rows_e = rows_o = list(range(L))
+    if ROW_ORDER == "fresh" and L % 2 == 0:
+        # E: rows 1, 3, 5.. open the windows 8, 10, 12.. that rows 2, 4, 6.. carry into; O: rows 2, 4, 6.. open the
+        # windows 9, 11, 13.. that rows 1, 3, 5.. carry into
+        rows_e = [0, 1] + [r for k in range(1, L // 2) for r in (2 * k + 1, 2 * k)]
+        rows_o = [0] + [r for k in range(1, L // 2) for r in (2 * k, 2 * k - 1)] + [L - 1]
+    for k in range(L):
+        i = rows_e[k]
+        _row_chain(asm, E, [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 0], n)
+        i = rows_o[k]
+        _row_chain(asm, O, [(i + j, a[j], b[i]) for j in range(L) if (i + j) % 2 == 1], n)
     return E, O
 
 
