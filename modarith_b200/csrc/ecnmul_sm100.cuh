@@ -125,7 +125,7 @@ template <class G, int PITCH = 0> struct EcnMul {
       const uint32_t cin = (n == 0) ? ((w == 0) ? 0u : (cprev >> 7) & 1u) : ((cwd >> (n - 1)) & 1u);
       const uint32_t cout = (cwd >> n) & 1u;
       const int d = (int)(((ew >> (4 * n)) & 0xfu) + cin) - (int)(cout << 4);
-      G::dbl(P, q); G::dbl(P, q); G::dbl(P, q); G::dbl(P, q);
+      G::dbl4(P, q);                  // P <- 16 P: four doublings, in whatever form the group does them fastest
       Pt Q;
       select(Q, tab, pitch, d);       // after the doublings: Q's 3L registers are not live across them
       G::add(P, Q, q);

@@ -25,6 +25,7 @@ template <class F> struct Edwards {
   static MAB_DEV Seq seq(uint32_t) { return Seq(); }
   static MAB_DEV void add(Pt& P, const Pt& Q, Seq&) { add(P, Q); }
   static MAB_DEV void dbl(Pt& P, Seq&) { dbl(P); }
+  static MAB_DEV void dbl4(Pt& P, Seq&) { dbl(P); dbl(P); dbl(P); dbl(P); }
   static MAB_DEV void add(Pt& P, const Pt& Q) {
     uint32_t A[L], B[L], C[L], D[L], E[L], Ff[L], Gg[L], dd[L];
     F::set_ed_d(dd);
