@@ -148,6 +148,23 @@ template <class F> struct Field {
     a[L - 1] = mab_shf_r(c[L - 1], carry, 1);
   }
 
+  // a/2 mod p for a value that is already in [0, p) (what the fully reduced plans store): no canonicalisation first
+  static MAB_DEV void haf_reduced(uint32_t (&a)[L]) {
+    uint32_t pw[L];
+    F::set_p(pw);
+    const uint32_t m = 0u - (a[0] & 1u);
+    uint32_t c[L], carry = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+      uint64_t t = (uint64_t)a[i] + (pw[i] & m) + carry;
+      c[i] = (uint32_t)t;
+      carry = (uint32_t)(t >> 32);
+    }
+#pragma unroll
+    for (int i = 0; i < L - 1; i++) a[i] = mab_shf_r(c[i], c[i + 1], 1);
+    a[L - 1] = mab_shf_r(c[L - 1], carry, 1);
+  }
+
   // modshl, pseudo.py:1052-1065.  The reference shifts raw limbs (no reduction; it has spare
   // bits).  Saturated limbs have none, so this is a * 2^n as a field element -- identical
   // wherever the reference's result is a legal (non-overflowing) element.
