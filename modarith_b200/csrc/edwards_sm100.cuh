@@ -26,6 +26,14 @@ template <class F> struct Edwards {
   static MAB_DEV void add(Pt& P, const Pt& Q, Seq&) { add(P, Q); }
   static MAB_DEV void dbl(Pt& P, Seq&) { dbl(P); }
   static MAB_DEV void dbl4(Pt& P, Seq&) { dbl(P); dbl(P); dbl(P); dbl(P); }
+  template <int N> static MAB_DEV void dbln(Pt& P, Seq&) {
+    for (int i = 0; i < N; i++) dbl(P);
+  }
+  // e*P + f*Q with joint 2-bit windows (EcnMul::mul2w; the 16-entry table lives in the global workspace)
+#ifndef MAB_ED_MUL2_WINDOW
+#define MAB_ED_MUL2_WINDOW 1
+#endif
+  static constexpr bool MUL2_WINDOW = (MAB_ED_MUL2_WINDOW != 0);
   static MAB_DEV void add(Pt& P, const Pt& Q) {
     uint32_t A[L], B[L], C[L], D[L], E[L], Ff[L], Gg[L], dd[L];
     F::set_ed_d(dd);

@@ -615,7 +615,10 @@ k_ecnmul2(const uint8_t* e, const uint8_t* x1, const uint8_t* y1, const uint8_t*
   typedef EcnMul<G, MAB_ECN_THREADS> M;
   uint4* tab;
   uint32_t* scr;
-  if (MAB_ECN_GLOBAL(G)) {
+  if (G::MUL2_WINDOW) {              // joint 2-bit windows: 16-entry table, always in the global workspace
+    tab = tabws + (size_t)blockIdx.x * (M::NE2W * 3 * (L / 4) * MAB_ECN_THREADS) + threadIdx.x;
+    scr = reinterpret_cast<uint32_t*>(mab_smem4) + threadIdx.x;
+  } else if (MAB_ECN_GLOBAL(G)) {
     tab = tabws + (size_t)blockIdx.x * (9 * 3 * (L / 4) * MAB_ECN_THREADS) + threadIdx.x;
     scr = reinterpret_cast<uint32_t*>(mab_smem4) + threadIdx.x;
   } else {
@@ -647,7 +650,8 @@ k_ecnmul2(const uint8_t* e, const uint8_t* x1, const uint8_t* y1, const uint8_t*
     aos_ld<L>(raw, f, i, align);
 #pragma unroll
     for (int j = 0; j < L; j++) fw[j] = mab_bswap(raw[L - 1 - j]);
-    M::mul2(R, ew, P, fw, Q, tab, MAB_ECN_THREADS, scr, align >> 16);
+    if (G::MUL2_WINDOW) M::mul2w(R, ew, P, fw, Q, tab, MAB_ECN_THREADS, scr, align >> 16);
+    else M::mul2(R, ew, P, fw, Q, tab, MAB_ECN_THREADS, scr, align >> 16);
     G::get(xw, yw, R);
 #pragma unroll
     for (int j = 0; j < L; j++) raw[L - 1 - j] = mab_bswap(xw[j]);

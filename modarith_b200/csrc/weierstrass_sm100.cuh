@@ -101,8 +101,8 @@ template <class F> struct Weierstrass {
     Fd::cpy(P.x, x3); Fd::cpy(P.y, y3); Fd::cpy(P.z, z3);
   }
 
-  // P <- 16 P, the four doublings between two digits of the window method (weierstrass.c:528-531 calls ecnXXXdbl
-  // four times).  The complete doubling above is 8M + 3S + 2 multiplications by b = 13 products; on a curve of prime
+  // P <- 2^N P: the four doublings between two digits of the window method (weierstrass.c:528-531 calls ecnXXXdbl
+  // four times), the two between joint digits of e*P + f*Q.  The complete doubling above is 8M + 3S + 2 multiplications by b = 13 products; on a curve of prime
   // order with a = -3 the Jacobian doubling (delta = Z^2, gamma = Y^2, beta = X gamma, alpha = 3 (X - delta)(X + delta),
   // X' = alpha^2 - 8 beta, Z' = (Y + Z)^2 - gamma - delta, Y' = alpha (4 beta - X') - 8 gamma^2: 3M + 5S) is valid
   // for EVERY point -- there is no point of order two, and infinity (Z = 0) stays at Z' = 0 -- so the run of four is
@@ -113,8 +113,14 @@ template <class F> struct Weierstrass {
 #ifndef MAB_ECN_JACOBIAN
 #define MAB_ECN_JACOBIAN 1
 #endif
-  static MAB_DEV void dbl4(Pt& P, Seq& q) {
-    if (!MAB_ECN_JACOBIAN) { dbl(P, q); dbl(P, q); dbl(P, q); dbl(P, q); return; }
+  static MAB_DEV void dbl4(Pt& P, Seq& q) { dbln<4>(P, q); }
+  // e*P + f*Q is done with joint 2-bit windows (EcnMul::mul2w): a 16-entry table in the global workspace
+  static constexpr bool MUL2_WINDOW = true;
+  template <int N> static MAB_DEV void dbln(Pt& P, Seq& q) {
+    if (!MAB_ECN_JACOBIAN) {
+      for (int i = 0; i < N; i++) dbl(P, q);
+      return;
+    }
     uint32_t X[L], Y[L], Z[L], d[L], g[L], b[L], a[L], t[L];
     sqrq(q, d, P.z);                               // delta = Z^2, also what the change of coordinates needs
     mulq(q, X, P.x, P.z);                          // X Z
@@ -126,7 +132,7 @@ template <class F> struct Weierstrass {
     // multiples 4 beta, 8 beta, 8 gamma^2 are gone); on this field an addition costs a quarter of a product.
     static_assert(F::MONTGOMERY, "haf_reduced below relies on fully reduced stored values");
     MAB_NOUNROLL
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < N; i++) {
       sqrq(q, g, Y);                               // gamma
       mulq(q, b, X, g);                            // beta
       F::sub(t, X, d);  F::add(a, X, d);

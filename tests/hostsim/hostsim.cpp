@@ -141,12 +141,13 @@ template <class F, class G> static void sim_ecnmul2(const unsigned char* e, cons
       w[k][pos >> 2] |= (uint32_t)src[k][b] << (8 * (pos & 3));
     }
   }
-  static uint4 tab[9 * 3 * L / 4];
+  static uint4 tab[16 * 3 * L / 4];
   static uint32_t scr[4 * (L + 1)];
   typename G::Pt P, Q, R;
   G::set(P, w[1], w[2]);
   G::set(Q, w[4], w[5]);
-  EcnMul<G>::mul2(R, w[0], P, w[3], Q, tab, 1, scr);
+  if (G::MUL2_WINDOW) EcnMul<G>::mul2w(R, w[0], P, w[3], Q, tab, 1, scr);
+  else EcnMul<G>::mul2(R, w[0], P, w[3], Q, tab, 1, scr);
   uint32_t xw[L], yw[L];
   G::get(xw, yw, R);
   for (int b = 0; b < 4 * L; b++) {
