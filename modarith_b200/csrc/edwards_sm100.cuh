@@ -14,6 +14,7 @@ template <class F> struct Edwards {
   // k_ecnmul: where the fixed-window table lives and how many CTAs per SM the registers are cut for (measured)
   static constexpr bool ECN_GLOBAL_TABLE = false;
   static constexpr int ECN_MINBLOCKS = 2;
+  static constexpr int ECN2_MINBLOCKS = 2;
 
   static MAB_DEV void inf(Pt& P) { Fd::zer(P.x); Fd::one(P.y); Fd::one(P.z); }           // edwards.c:170-175
   static MAB_DEV void cpy(Pt& R, const Pt& P) { Fd::cpy(R.x, P.x); Fd::cpy(R.y, P.y); Fd::cpy(R.z, P.z); }

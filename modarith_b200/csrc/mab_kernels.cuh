@@ -560,6 +560,11 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
 #else
 #define MAB_ECN_MB(G) (G::ECN_MINBLOCKS)
 #endif
+#ifdef MAB_ECN2_MINBLOCKS
+#define MAB_ECN2_MB(G) (MAB_ECN2_MINBLOCKS)
+#else
+#define MAB_ECN2_MB(G) (G::ECN2_MINBLOCKS)
+#endif
 #define MAB_ECN_THREADS 128
 // Persistent grid: CTA b handles the 128-point blocks b, b + gridDim.x, ...
 template <class F, class G> __global__ void __launch_bounds__(MAB_ECN_THREADS, MAB_ECN_MB(G))
@@ -607,7 +612,7 @@ k_ecnmul(const uint8_t* e, const uint8_t* x, const uint8_t* y, uint8_t* xo, uint
 // ecnXXXset x2 + ecnXXXmul2 + ecnXXXget (weierstrass.c:545-572 / edwards.c:486-513) for n independent
 // pairs: (xo, yo) = affine(e*(x1,y1) + f*(x2,y2)); same conventions and the same persistent grid /
 // table placement as k_ecnmul (the table has five entries here, the scratch column 4(L+1) words).
-template <class F, class G> __global__ void __launch_bounds__(MAB_ECN_THREADS, MAB_ECN_MB(G))
+template <class F, class G> __global__ void __launch_bounds__(MAB_ECN_THREADS, MAB_ECN2_MB(G))
 k_ecnmul2(const uint8_t* e, const uint8_t* x1, const uint8_t* y1, const uint8_t* f, const uint8_t* x2, const uint8_t* y2,
           uint8_t* xo, uint8_t* yo, size_t n, unsigned align, uint4* tabws) {
   constexpr int L = F::L;

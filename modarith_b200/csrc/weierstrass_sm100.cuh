@@ -16,9 +16,14 @@ template <class F> struct Weierstrass {
   static constexpr int L = F::L;
   typedef Field<F> Fd;
   struct Pt { uint32_t x[L], y[L], z[L]; };
-  // k_ecnmul: where the fixed-window table lives and how many CTAs per SM the registers are cut for (measured)
-  static constexpr bool ECN_GLOBAL_TABLE = true;
-  static constexpr int ECN_MINBLOCKS = 3;
+  // k_ecnmul: where the fixed-window table lives and how many CTAs per SM the registers are cut for (measured,
+  // profiles/r2_ecn_variants.txt).  Round 1 ran three CTAs at 168 registers (700 bytes of spill) with the table in
+  // a global workspace; with the Jacobian doubling runs the loop needs the registers more than the warps: two CTAs
+  // at 255 registers with the nine-entry table in shared memory (2 x 108 KB) give 21.6 M/s against 17.6 / 18.8
+  // (three CTAs / two CTAs with the global table).  k_ecnmul2 (sixteen-entry table, always global) stays at three.
+  static constexpr bool ECN_GLOBAL_TABLE = false;
+  static constexpr int ECN_MINBLOCKS = 2;
+  static constexpr int ECN2_MINBLOCKS = 3;
 
   static MAB_DEV void inf(Pt& P) { Fd::zer(P.x); Fd::one(P.y); Fd::zer(P.z); }          // weierstrass.c:283-288
   static MAB_DEV void cpy(Pt& R, const Pt& P) { Fd::cpy(R.x, P.x); Fd::cpy(R.y, P.y); Fd::cpy(R.z, P.z); }
