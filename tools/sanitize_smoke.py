@@ -53,5 +53,17 @@ for curve, gx, gy in (("NIST256", PRIMES["NIST256"].wgx, PRIMES["NIST256"].wgy),
     from modarith_b200.ecn import ecnmul2  # noqa: E402
     f = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
     ecnmul2(curve, e, x, y, f, xo, yo)
+# a batch large enough for the per-sub-partition work queues with stealing (>= 8 groups per SM)
+n = 148 * 8 * 32 + 77
+k = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+u = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+a = rfc7748("X25519", k, u)
+b = rfc7748("X25519", k[:1000].contiguous(), u[:1000].contiguous())
+assert torch.equal(a[:1000], b)
+# a straight-line program with its registers in shared memory
+F = Field("NIST256")
+x, _ = F.modimp(torch.randint(0, 256, (333, 32), dtype=torch.uint8, device="cuda", generator=g))
+y, _ = F.modimp(torch.randint(0, 256, (333, 32), dtype=torch.uint8, device="cuda", generator=g))
+F.modprog([("mul", 2, 0, 1), ("add", 3, 2, 0), ("sqr", 3, 3, 0), ("sub", 4, 3, 1), ("inv", 5, 4, 0), ("mli", 6, 5, 0, 7)], [x, y], [3, 5, 6])
 torch.cuda.synchronize()
 print("sanitize smoke done")
