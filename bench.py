@@ -136,9 +136,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self, t_begin=None, t_end=None):
-        """Summarise the samples whose timestamp falls inside [t_begin, t_end] (time.time() values
-        bracketing the timed region; the sampler itself is started before the warm-up)."""
+    def stop(self, t_begin=None, t_end=None, more=()):
+        """Summarise the samples whose timestamp falls inside [t_begin, t_end] or one of the `more` windows
+        (time.time() values bracketing the timed regions; the sampler itself is started before the warm-up)."""
         if self.proc is None:
             return None
         try:
@@ -162,7 +162,7 @@ class ClockSampler:
                     ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
                 except ValueError:
                     continue
-                if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                if not any(a - 0.02 <= ts <= b + 0.02 for a, b in ((t_begin, t_end),) + tuple(more)):
                     continue
             try:
                 sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
@@ -609,7 +609,6 @@ def main():
     barrier()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = args.steps
 
     # ---- end to end: host buffers through the C ABI (H2D + ladder + D2H inside the timed region) --
@@ -633,7 +632,12 @@ def main():
     staged_s, _ = run_e2e(max(3, args.steps // 2))
     staged_rate = n_local * max(3, args.steps // 2) / staged_s
     os.environ.pop("MAB_HOST_ZEROCOPY")
+    t2_begin = time.time()
     e2e_s, e2e_steps = run_e2e(args.steps)
+    t2_end = time.time()
+    # clocks: samples taken during either timed region (device-resident loop, end-to-end loop); nvidia-smi answers
+    # every 20-150 ms depending on the box, and ten 20 ms steps alone can see a single sample
+    clocks = sampler.stop(t_begin, t_end, more=((t2_begin, t2_end),)) if rank == 0 else None
     e2e_launches = args.steps
     if want0 is not None:
         # the host-buffer route on the same keys (one more call, outside the timed region)
