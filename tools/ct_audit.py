@@ -279,8 +279,11 @@ def analyse(name, ins):
         else:
             new = src_t
         for r in d["dests"]:
-            cc = {f for f in cc if not f.startswith(r + "?") and f.split("?")[1].lstrip("!") != r}
+            # facts guarded BY r die whenever r is written; facts ABOUT r survive a guarded clean definition (when it
+            # executes the new value is clean, when it does not the old fact still applies)
+            cc = {f for f in cc if f.split("?")[1].lstrip("!") != r}
             if g is None or new:
+                cc = {f for f in cc if not f.startswith(r + "?")}
                 for x in [x for x in t if x.startswith(r + ".b")]:
                     t.discard(x)
             if new:
@@ -289,13 +292,29 @@ def analyse(name, ins):
                 t.discard(r)
             elif r in t:
                 cc.add(r + "?" + g)
+                # `@P def` and `@!P def`, both from clean sources, define the register on every path
+                other = r + "?" + (g[1:] if g.startswith("!") else "!" + g)
+                if other in cc:
+                    t.discard(r)
+                    cc = {f for f in cc if not f.startswith(r + "?")}
         out = (frozenset(t), frozenset(cc))
+
+        def resolved(lit):
+            """the state on an edge along which predicate literal `lit` is known to hold: facts r?lit become plain"""
+            clean = {f.split("?")[0] for f in cc if f.split("?")[1] == lit}
+            return (frozenset(x for x in t if x not in clean), frozenset(cc))
+
         for j in succ[i]:
+            edge = out
+            if d["base"] == "BRA" and g is not None and d["target"] is not None and len(succ[i]) == 2:
+                # `@P BRA target`: P holds on the taken edge, !P on the fall-through
+                comp = g[1:] if g.startswith("!") else "!" + g
+                edge = resolved(g) if j == d["target"] and j != i + 1 else resolved(comp)
             if state_in[j] is None:
-                merged = out
+                merged = edge
             else:
                 # a fact about a register that is clean anyway on one side holds there vacuously
-                (ta, ca), (tb, cb) = state_in[j], out
+                (ta, ca), (tb, cb) = state_in[j], edge
                 keep = frozenset(f for f in (ca | cb)
                                  if (f in ca or f.split("?")[0] not in ta) and (f in cb or f.split("?")[0] not in tb))
                 merged = (ta | tb, keep)
