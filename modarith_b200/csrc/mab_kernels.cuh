@@ -401,11 +401,8 @@ template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k
 // amount of work whatever the batch size -- the multiplier pipe of a sub-partition is the resource, and a
 // batch of 1.7 rounds that lets some sub-partitions run two full rounds while others idle loses 13 %
 // (round 1: 0.87 of the large-batch rate at 2^17 keys).  Inside a queue the resident warps draw chunks
-// from an atomic counter.  A queue that is at most one round long (up to 4 groups per warp) is cut evenly, one
-// chunk per warp, so that every warp shares ONE inversion among all its keys (handing such a queue out in single
-// groups would cost an inversion per group: 4-5 % of a 2^17- or 2^18-key batch); longer queues get K = 4 chunks
-// first, then K = 2, single groups last, so that the warps the scheduler favoured (the sub-partition arbiter is
-// not fair) take more of them and all finish together.
+// from an atomic counter: K = 4 chunks first, then K = 2, single groups last, so that the warps the
+// scheduler favoured (the sub-partition arbiter is not fair) take more of them and all finish together.
 // A warp whose queue is empty steals from the other queues, which also makes the result independent of
 // where the CTAs were placed.  Small batches (grid below full residency) use one queue.
 #define MAB_LADDER_KMAX 4
@@ -417,10 +414,7 @@ struct MabQueues {
   // chunk list of a queue (see mab_queue_chunks on the host side) depends on its length only, so the host works
   // it out for the two lengths that occur: index 0 = base groups, index 1 = base + 1.
   unsigned base, rem;
-  // chunk list of a queue, for the two queue lengths that occur (s: base groups, l: base + 1), see mab_queue_chunk:
-  //   even = 0: c4 chunks of K = 4, then c2 chunks of K = 2, single groups up to the queue's end
-  //   even = 1: the whole queue is ONE round -- c2 chunks of c4 + 1 groups, then wq - c2 chunks of c4 groups
-  unsigned c4s, c2s, c4l, c2l, evens, evenl, wq;
+  unsigned c4s, c2s, c4l, c2l;     // K = 4 chunks, then K = 2 chunks (s: base groups, l: base + 1); single groups follow
 };
 // groups [lo, lo + g) of queue q; `longer` = 1 for the queues that hold base + 1 groups
 static __device__ __forceinline__ void mab_queue_range(const MabQueues& Q, unsigned q, unsigned long long& lo, unsigned& g, unsigned& longer) {
@@ -429,18 +423,7 @@ static __device__ __forceinline__ void mab_queue_range(const MabQueues& Q, unsig
   g = Q.base + longer;
 }
 // chunk ci of a queue: returns K (0 = past the end) and the first group of the chunk inside the queue
-static __device__ __forceinline__ unsigned mab_queue_nchunks(unsigned g, unsigned c4, unsigned c2, unsigned even, unsigned wq) {
-  if (even) return c4 ? wq : c2;
-  return c4 + c2 + (g - 4 * c4 - 2 * c2);
-}
-static __device__ __forceinline__ int mab_queue_chunk(unsigned g, unsigned c4, unsigned c2, unsigned even, unsigned wq,
-                                                      unsigned long long ci, unsigned& first) {
-  if (even) {                        // c2 chunks of c4 + 1 groups, then chunks of c4 groups
-    if (ci < c2) { first = (unsigned)ci * (c4 + 1); return (int)(c4 + 1); }
-    if (c4 == 0 || ci >= wq) return 0;
-    first = c2 * (c4 + 1) + (unsigned)(ci - c2) * c4;
-    return (int)c4;
-  }
+static __device__ __forceinline__ int mab_queue_chunk(unsigned g, unsigned c4, unsigned c2, unsigned long long ci, unsigned& first) {
   if (ci < c4) { first = (unsigned)ci * 4; return 4; }
   if (ci < (unsigned long long)c4 + c2) { first = c4 * 4 + (unsigned)(ci - c4) * 2; return 2; }
   const unsigned long long s = (unsigned long long)c4 * 4 + (unsigned long long)c2 * 2 + (ci - c4 - c2);
@@ -486,8 +469,8 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
             if (qq >= Q.nq) qq -= Q.nq;
             unsigned long long lo2; unsigned g2, lg2;
             mab_queue_range(Q, qq, lo2, g2, lg2);
-            const unsigned c4 = lg2 ? Q.c4l : Q.c4s, c2 = lg2 ? Q.c2l : Q.c2s, ev = lg2 ? Q.evenl : Q.evens;
-            has = *(volatile unsigned long long*)(Q.counter + qq) < (unsigned long long)mab_queue_nchunks(g2, c4, c2, ev, Q.wq);
+            const unsigned c4 = lg2 ? Q.c4l : Q.c4s, c2 = lg2 ? Q.c2l : Q.c2s;
+            has = *(volatile unsigned long long*)(Q.counter + qq) < (unsigned long long)(c4 + c2 + (g2 - 4 * c4 - 2 * c2));
           }
           const unsigned m = __ballot_sync(0xffffffffu, has);
           if (m) {
@@ -503,8 +486,8 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
       }
       unsigned g, longer;
       mab_queue_range(Q, q, glo, g, longer);
-      const unsigned c4 = longer ? Q.c4l : Q.c4s, c2 = longer ? Q.c2l : Q.c2s, ev = longer ? Q.evenl : Q.evens;
-      const unsigned nchunks = mab_queue_nchunks(g, c4, c2, ev, Q.wq);
+      const unsigned c4 = longer ? Q.c4l : Q.c4s, c2 = longer ? Q.c2l : Q.c2s;
+      const unsigned nchunks = c4 + c2 + (g - 4 * c4 - 2 * c2);
       unsigned long long ci = 0;
       int ok = 0;
       if (lane == 0) {
@@ -517,7 +500,7 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
       ok = __shfl_sync(0xffffffffu, ok, 0);
       if (ok) {
         ci = __shfl_sync(0xffffffffu, ci, 0);
-        K = mab_queue_chunk(g, c4, c2, ev, Q.wq, ci, first);
+        K = mab_queue_chunk(g, c4, c2, ci, first);
         if (K) break;
       }
       // this queue is empty: the home queue is left for good; a stolen-from queue is swept past
