@@ -347,6 +347,14 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
                 ("mul", Z3, t4, Z3), ("mul", t1, t3, t0), ("add", Z3, Z3, t1)]
         outs = [F.alloc(m) for _ in range(3)]
         t = _time(lambda: F.modprog(code, ops, [X3, Y3, Z3], outputs=outs), 3)
+        try:
+            outs_j = [F.alloc(m) for _ in range(3)]
+            F.modprog(code, ops, [X3, Y3, Z3], outputs=outs_j, jit=True)           # compiles (about a second), then cached
+            tj = _time(lambda: F.modprog(code, ops, [X3, Y3, Z3], outputs=outs_j, jit=True), 3)
+            same = all(bool(torch.equal(a, b)) for a, b in zip(outs, outs_j))
+            del outs_j
+        except Exception as ex:
+            tj, same = None, str(ex)[:200]
         R = [F.alloc(m) for _ in range(15)]
         for k in range(7):
             R[k].copy_(ops[k])
@@ -360,7 +368,12 @@ def extra_measurements(lib, mlib, dev, peak, hbm_peak):
             "workload": "complete P-256 point addition as a 43-instruction modprog program, 2^21 point pairs",
             "value": m / t, "unit": "additions/s", "one_launch_per_call_value": m / ts, "speedup": ts / t,
             "field_ops_per_s": m * len(code) / t, "imad_frac": (m / t * nmul * 64 / pk) if pk else None,
-            "hbm_bytes_per_addition": 10 * 32, "one_launch_per_call_hbm_bytes": len(code) * 96}
+            "hbm_bytes_per_addition": 10 * 32, "one_launch_per_call_hbm_bytes": len(code) * 96,
+            "compiled": {"note": "mab_NIST256_modprog_jit: the same program compiled by NVRTC, variables in machine registers",
+                         "value": (m / tj) if tj else None, "unit": "additions/s",
+                         "imad_frac": (m / tj * nmul * 64 / pk) if (tj and pk) else None,
+                         "speedup_over_one_launch_per_call": (ts / tj) if tj else None,
+                         "identical_to_interpreted": same}}
         del ops, outs, R
     except Exception as ex:
         out["nist256_modprog_point_addition"] = {"error": str(ex)[:200]}

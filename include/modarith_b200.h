@@ -46,6 +46,8 @@ extern "C" {
 
 #define MAB_ERR_BADARG 100001
 #define MAB_ERR_NODEVICE 100002
+#define MAB_ERR_NOJIT 100003 /* mab_<P>_modprog_jit: the run-time compiler (NVRTC) could not be loaded */
+#define MAB_ERR_JIT 100004   /* mab_<P>_modprog_jit: compilation failed; mab_jit_log() has the compiler's output */
 
 /* ---- library-wide ---------------------------------------------------------------------- */
 MAB_API const char *mab_version(void);
@@ -54,6 +56,8 @@ MAB_API int mab_device_count(void);
 /* The *_host entry points keep three streams and staging buffers per device between calls;
  * this frees them (optional; they are also reclaimed at process exit). */
 MAB_API void mab_release_workspaces(void);
+/* Output of the run-time compiler for the calling thread's last mab_<P>_modprog_jit / _modprog_cubin call. */
+MAB_API const char *mab_jit_log(void);
 /* Parameters of a modulus by name ("X25519", ...): Wordlength/Nlimbs/Radix/Nbits/Nbytes macros
  * of the generated header (pseudo.py:1403-1407).  Returns 0, or MAB_ERR_BADARG. */
 MAB_API int mab_params(const char *prime, int *wordlength, int *nlimbs, int *radix, int *nbits, int *nbytes);
@@ -112,6 +116,17 @@ typedef struct mab_insn {
   unsigned char op, dst, a, b; /* enum mab_opcode, then register numbers 0 .. MAB_PROG_NREG-1 */
   uint32_t imm;                /* small-integer operand of MLI / NSQR / INT */
 } mab_insn;
+/* Compiled programs (mab_<P>_modprog_jit).  The reference's model is textual: the generator prints functions, the
+ * consumer pastes them into its source and compiles (pseudo.py:1694-1702; rfc7748.c:24-28, weierstrass.c:16-20).
+ * mab_<P>_modprog_jit does that for a program handed over at run time: it prints a kernel that calls the generated
+ * functions on variables held in MACHINE REGISTERS, compiles it with NVRTC for sm_100a against the headers the
+ * library itself was built from (embedded as text) and caches the loaded kernel, keyed by the program.  The first
+ * call of a new program costs a compilation (about a second); every later call is one launch.  Same instruction
+ * set, arguments and bit-identical results as mab_<P>_modprog, which interprets the program with its variables in
+ * shared memory and needs no compiler.  NVRTC is loaded on first use (libnvrtc.so.12, or the path in the
+ * environment variable MAB_NVRTC); without it the call returns MAB_ERR_NOJIT -- there is no silent fall-back.
+ * mab_<P>_modprog_cubin returns the compiled cubin of a program for inspection (needs no device): *size is the
+ * capacity of buf on entry and the cubin's size on return; buf may be NULL to ask for the size. */
 
 /* ---- per-modulus API (P = X25519, X448, NIST256) ------------------------------------------ */
 #define MAB_DECLARE_FIELD(P)                                                                              \
@@ -176,7 +191,12 @@ typedef struct mab_insn {
   MAB_API int mab_##P##_modcmp(const uint32_t *a, const uint32_t *b, int *out, size_t n, size_t stride, void *stream); \
   /* a sequence of the calls above in one launch, see "straight-line programs" */                       \
   MAB_API int mab_##P##_modprog(const mab_insn *code, size_t ncode, const uint32_t *const *in, int nin, uint32_t *const *out, \
-                                const unsigned char *out_reg, int nout, size_t n, size_t stride, void *stream);
+                                const unsigned char *out_reg, int nout, size_t n, size_t stride, void *stream); \
+  /* the same program COMPILED: see "compiled programs" above.  Same arguments, same results */         \
+  MAB_API int mab_##P##_modprog_jit(const mab_insn *code, size_t ncode, const uint32_t *const *in, int nin, uint32_t *const *out, \
+                                    const unsigned char *out_reg, int nout, size_t n, size_t stride, void *stream); \
+  MAB_API int mab_##P##_modprog_cubin(const mab_insn *code, size_t ncode, int nin, const unsigned char *out_reg, int nout, \
+                                      void *buf, size_t *size);
 
 MAB_DECLARE_FIELD(X25519)
 MAB_DECLARE_FIELD(X448)

@@ -20,10 +20,43 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmodarith_b200.so")
 OBJDIR = os.path.join(PKG, "build")
 
-NVCC_FLAGS = ["-I", CSRC, "-I", os.path.join(PKG, "..", "include"), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-I", CSRC, "-I", os.path.join(PKG, "..", "include"), "-I", OBJDIR, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 UNITS = ["mab_capi_X25519.cu", "mab_capi_X448.cu", "mab_capi_NIST256.cu", "mab_capi_SECP256K1.cu",
-         "mab_capi_NIST256ORDER.cu", "mab_runtime.cu"]
+         "mab_capi_NIST256ORDER.cu", "mab_runtime.cu", "mab_jit.cu"]
+# headers handed to NVRTC by mab_<P>_modprog_jit: embedded in the library as text (csrc/mab_jit.h)
+JIT_COMMON = ["mab_common.cuh", "mab_field.cuh"]
+JIT_FIELDS = ["X25519", "X448", "NIST256", "SECP256K1", "NIST256ORDER"]
+
+
+def _as_literal(sym, text):
+    """A C++ array initialised from adjacent raw string literals (chunks of whole lines, each far below any
+    compiler's literal limit)."""
+    assert ')MABJIT"' not in text
+    out, chunk, size = ["static const char %s[] =" % sym], [], 0
+    for line in text.splitlines(keepends=True):
+        chunk.append(line)
+        size += len(line)
+        if size > 8000:
+            out.append('R"MABJIT(' + "".join(chunk) + ')MABJIT"')
+            chunk, size = [], 0
+    out.append('R"MABJIT(' + "".join(chunk) + ')MABJIT";')
+    return "\n".join(out) + "\n"
+
+
+def _write_if_changed(path, text):
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
+
+
+def write_jit_sources():
+    os.makedirs(OBJDIR, exist_ok=True)
+    text = "".join(_as_literal("kJitSrc_" + fn.split(".")[0], open(os.path.join(CSRC, fn)).read()) for fn in JIT_COMMON)
+    _write_if_changed(os.path.join(OBJDIR, "jit_src_common.inc"), text)
+    for P in JIT_FIELDS:
+        src = open(os.path.join(CSRC, "gen", "field_%s.cuh" % P)).read()
+        _write_if_changed(os.path.join(OBJDIR, "jit_src_%s.inc" % P), _as_literal("kJitSrc_field", src))
 
 
 def _nvcc():
@@ -54,6 +87,7 @@ def build(force=False, verbose=True):
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
+    write_jit_sources()
     nvcc = _nvcc()
 
     def compile_one(unit):
@@ -68,7 +102,7 @@ def build(force=False, verbose=True):
 
     with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)

@@ -4,4 +4,5 @@
 #define MAB_F F_NIST256
 #define MAB_HAS_WEIERSTRASS 1
 
+#define MAB_JIT_SRC "jit_src_NIST256.inc"
 #include "mab_capi.inc"

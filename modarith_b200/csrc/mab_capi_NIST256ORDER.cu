@@ -2,4 +2,5 @@
 #include "gen/field_NIST256ORDER.cuh"
 #define MAB_P NIST256ORDER
 #define MAB_F F_NIST256ORDER
+#define MAB_JIT_SRC "jit_src_NIST256ORDER.inc"
 #include "mab_capi.inc"

@@ -4,4 +4,5 @@
 #define MAB_F F_X25519
 #define MAB_HAS_CURVE 1
 #define MAB_HAS_EDWARDS 1
+#define MAB_JIT_SRC "jit_src_X25519.inc"
 #include "mab_capi.inc"

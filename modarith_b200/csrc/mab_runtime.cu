@@ -11,6 +11,7 @@
 #include "gen/field_NIST256.cuh"
 #include "mab_probe.cuh"
 #include "mab_workspace.h"
+#include "mab_jit.h"
 #include "mab_unsat29.cuh"
 #include <mutex>
 
@@ -232,10 +233,13 @@ const char* mab_error_string(int code) {
   if (code == 0) return "ok";
   if (code == MAB_ERR_BADARG) return "modarith_b200: bad argument";
   if (code == MAB_ERR_NODEVICE) return "modarith_b200: no CUDA device";
+  if (code == MAB_ERR_NOJIT) return "modarith_b200: NVRTC (libnvrtc.so.12) could not be loaded; see mab_jit_log()";
+  if (code == MAB_ERR_JIT) return "modarith_b200: run-time compilation failed; see mab_jit_log()";
   return cudaGetErrorString((cudaError_t)code);
 }
 
 void mab_release_workspaces(void) {
+  mab_jit_release();
   {
     std::lock_guard<std::mutex> g(g_counter_mutex);
     int prev = 0;

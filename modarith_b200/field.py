@@ -213,21 +213,12 @@ class Field:
         return out
 
     # -- a sequence of the calls above in ONE launch (mab_<P>_modprog) ---------------------------
-    def modprog(self, code, inputs, out_regs, outputs=None):
-        """Run a straight-line program with its variables held on chip.
-
-        code     : [(op, dst, a, b)] or [(op, dst, a, b, imm)] with op one of add sub neg mul sqr mli cpy nsqr pro
-                   inv sqrt zer one int haf; dst / a / b are register numbers 0..15 (unused ones may be 0);
-                   semantics of each op = the API function of the same name
-        inputs   : limb-plane tensors, loaded into registers 0, 1, ... before the first instruction
-        out_regs : registers to store after the last instruction; returns one plane tensor per entry
-                   (written into `outputs` when given)
-        E.g. (x + y)^2 - x*y:  F.modprog([("add", 2, 0, 1), ("sqr", 2, 2, 0), ("mul", 3, 0, 1), ("sub", 2, 2, 3)], [x, y], [2])"""
-        import ctypes
+    @staticmethod
+    def _encode_program(code, out_regs):
         if not code or len(code) > _lib.PROG_MAX:
             raise ValueError("a program has 1 .. %d instructions" % _lib.PROG_MAX)
-        if len(inputs) > _lib.PROG_NREG or len(out_regs) > _lib.PROG_NREG or not out_regs:
-            raise ValueError("at most %d inputs and 1 .. %d outputs" % (_lib.PROG_NREG, _lib.PROG_NREG))
+        if len(out_regs) > _lib.PROG_NREG or not out_regs:
+            raise ValueError("1 .. %d outputs" % _lib.PROG_NREG)
         arr = (_lib.mab_insn * len(code))()
         for k, ins in enumerate(code):
             if len(ins) not in (4, 5) or ins[0] not in _lib.OPCODES:
@@ -241,6 +232,47 @@ class Field:
             arr[k].op, arr[k].dst, arr[k].a, arr[k].b, arr[k].imm = _lib.OPCODES[ins[0]], regs[0], regs[1], regs[2], imm
         if any((not isinstance(r, int)) or r < 0 or r >= _lib.PROG_NREG for r in out_regs):
             raise ValueError("output registers are 0 .. %d" % (_lib.PROG_NREG - 1))
+        return arr
+
+    @classmethod
+    def modprog_cubin(cls, prime, code, nin, out_regs):
+        """The sm_100a cubin mab_<P>_modprog_jit compiles for this program (bytes).  Needs NVRTC, no device."""
+        import ctypes
+        lib = _lib.load()
+        arr = cls._encode_program(code, out_regs)
+        if not (0 <= nin <= _lib.PROG_NREG):
+            raise ValueError("at most %d inputs" % _lib.PROG_NREG)
+        regs_p = (ctypes.c_ubyte * len(out_regs))(*out_regs)
+        fn = getattr(lib, "mab_%s_modprog_cubin" % prime)
+        cap = 1 << 22
+        while True:
+            buf = ctypes.create_string_buffer(cap)
+            size = ctypes.c_size_t(cap)
+            rc = fn(arr, len(code), nin, regs_p, len(out_regs), buf, ctypes.byref(size))
+            if rc != 0 and size.value > cap:          # the cubin is larger than the buffer: its size came back
+                cap = size.value
+                continue
+            _lib.check(rc, "mab_%s_modprog_cubin" % prime)
+            return buf.raw[:size.value]
+
+    def modprog(self, code, inputs, out_regs, outputs=None, jit=False):
+        """Run a straight-line program with its variables held on chip.
+
+        jit=False: mab_<P>_modprog, the interpreter (variables in shared memory, no compiler needed);
+        jit=True : mab_<P>_modprog_jit, the program compiled by NVRTC into a kernel of its own (variables in machine
+                   registers; the first call of a new program compiles, later calls hit the cache).  Same results.
+
+        code     : [(op, dst, a, b)] or [(op, dst, a, b, imm)] with op one of add sub neg mul sqr mli cpy nsqr pro
+                   inv sqrt zer one int haf; dst / a / b are register numbers 0..15 (unused ones may be 0);
+                   semantics of each op = the API function of the same name
+        inputs   : limb-plane tensors, loaded into registers 0, 1, ... before the first instruction
+        out_regs : registers to store after the last instruction; returns one plane tensor per entry
+                   (written into `outputs` when given)
+        E.g. (x + y)^2 - x*y:  F.modprog([("add", 2, 0, 1), ("sqr", 2, 2, 0), ("mul", 3, 0, 1), ("sub", 2, 2, 3)], [x, y], [2])"""
+        import ctypes
+        if len(inputs) > _lib.PROG_NREG:
+            raise ValueError("at most %d inputs" % _lib.PROG_NREG)
+        arr = self._encode_program(code, out_regs)
         ref = self._chk(*inputs) if inputs else None
         if outputs is None:
             if ref is None:
@@ -256,7 +288,7 @@ class Field:
         out_p = (ctypes.c_void_p * len(outputs))(*[t.data_ptr() for t in outputs])
         regs_p = (ctypes.c_ubyte * len(out_regs))(*out_regs)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        name = "mab_%s_modprog" % self.prime
+        name = "mab_%s_modprog%s" % (self.prime, "_jit" if jit else "")
         with torch.cuda.device(self.device):
             _lib.check(getattr(self.lib, name)(arr, len(code), ins_p, len(inputs), out_p, regs_p, len(outputs), n,
                                                max(stride, n), stream), name)

@@ -68,6 +68,7 @@ class mab_insn(ctypes.Structure):
 OPCODES = {n: i for i, n in enumerate(("add", "sub", "neg", "mul", "sqr", "mli", "cpy", "nsqr", "pro", "inv", "sqrt",
                                        "zer", "one", "int", "haf"))}
 PROG_NREG, PROG_MAX = 16, 320
+ERR_NOJIT, ERR_JIT = 100003, 100004
 
 _lib = None
 
@@ -106,6 +107,14 @@ def load() -> ctypes.CDLL:
         fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
                        c_int, c_size_t, c_size_t, c_void_p]
         fn.restype = c_int
+        fn = getattr(lib, "mab_%s_modprog_jit" % P)
+        fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
+                       c_int, c_size_t, c_size_t, c_void_p]
+        fn.restype = c_int
+        fn = getattr(lib, "mab_%s_modprog_cubin" % P)
+        fn.argtypes = [POINTER(mab_insn), c_size_t, c_int, POINTER(ctypes.c_ubyte), c_int, c_void_p, POINTER(c_size_t)]
+        fn.restype = c_int
+    lib.mab_jit_log.restype = c_char_p
     lib.mab_NIST256_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
     lib.mab_NIST256_ecnmul.restype = c_int
     lib.mab_ED25519_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
@@ -135,10 +144,10 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     """Every symbol include/modarith_b200.h declares (used by the CPU-side ABI test)."""
     syms = ["mab_version", "mab_error_string", "mab_device_count", "mab_params", "mab_products", "mab_imad_peak",
-            "mab_pipe_probe", "mab_release_workspaces", "mab_probe_unsat29_modmul",
+            "mab_pipe_probe", "mab_release_workspaces", "mab_probe_unsat29_modmul", "mab_jit_log",
             "mab_NIST256_ecnmul", "mab_ED25519_ecnmul", "mab_NIST256_ecnmul2", "mab_ED25519_ecnmul2"]
     for P in PRIMES:
-        syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES] + ["mab_%s_modprog" % P]
+        syms += ["mab_%s_%s" % (P, n) for n in FIELD_SIGNATURES] + ["mab_%s_modprog" % P, "mab_%s_modprog_jit" % P, "mab_%s_modprog_cubin" % P]
     for P in CURVES:
         syms += ["mab_%s_rfc7748" % P, "mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_validate" % P,
                  "mab_%s_rfc7748_perkey" % P, "mab_%s_rfc7748_host_multi" % P]
@@ -148,6 +157,8 @@ def exported_symbols():
 def check(code: int, what: str = ""):
     if code != 0:
         msg = load().mab_error_string(code).decode()
+        if code in (ERR_NOJIT, ERR_JIT):
+            msg += "\n" + load().mab_jit_log().decode(errors="replace")[-4000:]
         raise MabError("%s failed: %s (code %d)" % (what or "modarith_b200 call", msg, code))
 
 

@@ -31,7 +31,7 @@ def header_symbols():
 def test_library_exports_every_declared_symbol(built):
     dll = ctypes.CDLL(built)
     want = header_symbols()
-    assert len(want) == 13 + 5 * 34 + 10
+    assert len(want) == 14 + 5 * 36 + 10
     for s in sorted(want):
         assert hasattr(dll, s), s
     assert want == set(mlib.exported_symbols())

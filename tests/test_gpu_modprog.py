@@ -103,7 +103,8 @@ def test_random_programs_against_separate_calls_and_oracle(name):
             assert ints == R, (name, trial, i)
 
 
-def test_weierstrass_addition_as_one_program():
+@pytest.mark.parametrize("jit", [False, True], ids=["interpreted", "compiled"])
+def test_weierstrass_addition_as_one_program(jit):
     """The complete projective addition for a = -3 (eprint 2015/1060 Algorithm 4, which weierstrass.c:69-160 transcribes)
     written as a modprog program over 12 registers: 12 multiplications, 2 by the curve constant b, 29 additions /
     subtractions -- one launch instead of 43.  Checked against affine arithmetic on the curve."""
@@ -153,7 +154,7 @@ def test_weierstrass_addition_as_one_program():
             ("mul", Z3, t4, Z3), ("mul", t1, t3, t0), ("add", Z3, Z3, t1),
             # affine: x = X3/Z3, y = Y3/Z3 (0 -> 0 gives (0, 0) for the point at infinity)
             ("inv", t0, Z3, 0), ("mul", X3, X3, t0), ("mul", Y3, Y3, t0)]
-    outs = F.modprog(code, [X1, Y1, one, X2, Y2, one, Bc], [X3, Y3, Z3])
+    outs = F.modprog(code, [X1, Y1, one, X2, Y2, one, Bc], [X3, Y3, Z3], jit=jit)
     xs, ys, zs = F.to_ints(outs[0]), F.to_ints(outs[1]), F.to_ints(outs[2])
     for i in range(n):
         want = affine_add(pts1[i], pts2[i])
@@ -164,29 +165,82 @@ def test_weierstrass_addition_as_one_program():
     assert zs[1] == 0 and (xs[0], ys[0]) == affine_add(pts1[0], pts1[0])
 
 
-def test_modprog_arguments():
+@pytest.mark.parametrize("jit", [False, True], ids=["interpreted", "compiled"])
+def test_modprog_arguments(jit):
     F = _field("X25519")
     x = F.from_ints([1, 2, 3])
     with pytest.raises(ValueError):
-        F.modprog([], [x], [0])
+        F.modprog([], [x], [0], jit=jit)
     with pytest.raises(ValueError):
-        F.modprog([("mul", 16, 0, 0)], [x], [0])
+        F.modprog([("mul", 16, 0, 0)], [x], [0], jit=jit)
     with pytest.raises(ValueError):
-        F.modprog([("frobnicate", 1, 0, 0)], [x], [0])
+        F.modprog([("frobnicate", 1, 0, 0)], [x], [0], jit=jit)
     with pytest.raises(ValueError):
-        F.modprog([("mli", 1, 0, 0, -1)], [x], [0])
+        F.modprog([("mli", 1, 0, 0, -1)], [x], [0], jit=jit)
     with pytest.raises(ValueError):
-        F.modprog([("mul", 1, 0, 0)] * 400, [x], [1])
-    out = F.modprog([("mul", 1, 0, 0), ("add", 1, 1, 0)], [x], [1])
+        F.modprog([("mul", 1, 0, 0)] * 400, [x], [1], jit=jit)
+    out = F.modprog([("mul", 1, 0, 0), ("add", 1, 1, 0)], [x], [1], jit=jit)
     assert F.to_ints(out[0]) == [2, 6, 12]
     # in place: the output tensor is an input
-    F.modprog([("sqr", 0, 0, 0)], [x], [0], outputs=[x])
+    F.modprog([("sqr", 0, 0, 0)], [x], [0], outputs=[x], jit=jit)
     assert F.to_ints(x) == [1, 4, 9]
     # ragged size across several blocks, pitch wider than n
     n = 1000
     wide = torch.zeros((F.Nlimbs, 3 * n), dtype=torch.int32, device="cuda")
     a, c = wide[:, :n], wide[:, 2 * n:]
     a.copy_(F.from_ints(list(range(n))))
-    F.modprog([("mli", 1, 0, 0, 3), ("add", 1, 1, 0)], [a], [1], outputs=[c])
+    F.modprog([("mli", 1, 0, 0, 3), ("add", 1, 1, 0)], [a], [1], outputs=[c], jit=jit)
     assert F.to_ints(c.contiguous()) == [4 * v for v in range(n)]
     assert int(wide[:, n:2 * n].abs().sum()) == 0
+
+
+def _random_program(rng, length, heavy):
+    ops2, ops1 = ["add", "sub", "mul"], ["neg", "sqr", "cpy", "haf"]
+    code, live = [], 3
+    for _ in range(length):
+        r = rng.random()
+        d = rng.randrange(16)
+        if r < 0.6:
+            code.append((rng.choice(ops2), d, rng.randrange(live), rng.randrange(live)))
+        elif r < 0.8:
+            code.append((rng.choice(ops1), d, rng.randrange(live), 0))
+        elif r < 0.87:
+            code.append(("mli", d, rng.randrange(live), 0, rng.choice([0, 1, 2, 121665, 39081, (1 << 31) - 1])))
+        elif r < 0.92:
+            code.append(("nsqr", d, rng.randrange(live), 0, rng.randrange(0, 5)))
+        elif r < 0.96:
+            code.append((rng.choice(["zer", "one"]), d, 0, 0))
+        else:
+            code.append(("int", d, 0, 0, rng.randrange(1 << 20)))
+        live = max(live, min(16, d + 1)) if d <= live else live
+    if heavy:
+        code += [("inv", 5, 0, 0), ("sqrt", 6, 1, 0), ("pro", 7, 2, 0)]
+    return code
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_compiled_programs_equal_interpreted_ones(name):
+    """mab_<P>_modprog_jit against mab_<P>_modprog on random programs: the same generated functions called in the same
+    order, so the limb planes -- not just the canonical values -- are bit-identical.  Registers that are never written
+    read as zero in both; a program is compiled once and then served from the cache (second call, other batch size)."""
+    F = _field(name)
+    p = FieldOracle(name).p
+    rng = random.Random(2024)
+    n = 1000
+    vals = [[rng.randrange(p) for _ in range(n)] for _ in range(3)]
+    for v in vals:
+        v[0], v[1], v[2] = 0, 1, p - 1
+    inputs = [F.from_ints(v) for v in vals]
+    for trial in range(2):
+        # the long fixed exponentiations inline ~270 products each; on the fall-back plan (500 instructions per
+        # product) that is a minute of compilation, so the group order gets the light programs only
+        code = _random_program(rng, 30, heavy=(trial == 0 and name != "NIST256ORDER"))
+        outs = list(range(16))
+        want = F.modprog(code, inputs, outs)
+        got = F.modprog(code, inputs, outs, jit=True)
+        for r in range(16):
+            assert torch.equal(got[r], want[r]), (name, trial, r)
+        small = [t[:, :77].contiguous() for t in inputs]
+        got2 = F.modprog(code, small, outs, jit=True)
+        for r in range(16):
+            assert torch.equal(got2[r], want[r][:, :77]), (name, trial, r, "cached kernel, other n")
