@@ -204,9 +204,9 @@ MAB_DECLARE_FIELD(NIST256)
 /* Two moduli outside the three hot-path ones: the secp256k1 field prime 2^256 - 2^32 - 977 (monty.py:2066-2067;
  * here a plain-residue plan that folds 2^256 == 2^32 + 977) and the order of the P-256 group (the reference's
  * "00<decimal>" mode, monty.py:2110-2127; the generator's fall-back plan: full Montgomery, any odd modulus,
- * monty.py:2237-2244).  Further moduli: print the header with
- *   python -m modarith_b200.gen.monty_sm100 "<expression>" -o field_NAME.cuh
- * and compile it behind this ABI with the three-line unit shown in INTEGRATION.md ("Textual inclusion and further moduli"). */
+ * monty.py:2237-2244).  Further moduli: `python -m modarith_b200.build --prime NAME[=<expression>]` builds an add-on
+ * library libmodarith_b200_<NAME>.so that exports MAB_DECLARE_FIELD(NAME) ("Textual inclusion and
+ * further moduli"). */
 MAB_DECLARE_FIELD(SECP256K1)
 MAB_DECLARE_FIELD(NIST256ORDER)
 

@@ -5,6 +5,8 @@ The reference's build step is "run the generator, compile what it printed"
 
     python -m modarith_b200.build            # regenerate + compile if stale
     python -m modarith_b200.build --force
+    python -m modarith_b200.build --prime NIST384            # add-on library for another modulus of the reference's
+    python -m modarith_b200.build --prime MYP="2**414-17"    # tables, or for any prime given as an expression
 """
 from __future__ import annotations
 
@@ -111,5 +113,63 @@ def build(force=False, verbose=True):
     return LIB
 
 
+def extra_lib_path(name):
+    return os.path.join(PKG, "libmodarith_b200_%s.so" % name)
+
+
+def build_extra(name, expr=None, force=False, verbose=True):
+    """An add-on library with the field entry points (mab_<NAME>_modmul, ..., _modprog, _modprog_jit) for a modulus
+    that is not one of the five built in: the reference's `python3 monty.py 64 NIST384` + compile, in one step
+    (pseudo.py:1694-1702).  Same C ABI, same kernels (csrc/mab_capi.inc instantiated on the generated header), linked
+    with the library's own runtime objects so that it stands alone: modarith_b200/libmodarith_b200_<NAME>.so, which
+    Field(NAME) loads.  `expr`: a Python integer expression for a modulus the tables do not name."""
+    import re
+    from .gen.cli import generate
+    from .primes import Prime, named
+    if not re.fullmatch(r"[A-Za-z][A-Za-z0-9]*", name):
+        raise ValueError("a modulus name is an identifier (it becomes part of the C symbols): %r" % name)
+    if expr is not None:
+        p = eval(expr, {"__builtins__": {}})
+        P = Prime(name, int(p), "monty")
+    else:
+        P = named(name)
+    build(verbose=False)                                   # the runtime objects and the common JIT sources
+    ext = os.path.join(OBJDIR, "ext")
+    os.makedirs(ext, exist_ok=True)
+    hdr = os.path.join(ext, "field_%s.cuh" % name)
+    generate(P, hdr, verbose=False)
+    unit = os.path.join(ext, "mab_capi_%s.cu" % name)
+    _write_if_changed(unit, '// C ABI instantiation for %s (python -m modarith_b200.build --prime)\n#include "field_%s.cuh"\n'
+                      '#include "modarith_b200.h"\nextern "C" {\nMAB_DECLARE_FIELD(%s)      // exported like the built-in moduli\n}\n'
+                      '#define MAB_P %s\n#define MAB_F F_%s\n#define MAB_JIT_SRC "jit_src_%s.inc"\n#include "mab_capi.inc"\n'
+                      % (name, name, name, name, name, name))
+    _write_if_changed(os.path.join(ext, "jit_src_%s.inc" % name), _as_literal("kJitSrc_field", open(hdr).read()))
+    out = extra_lib_path(name)
+    stamp = os.path.join(ext, "digest_%s.txt" % name)
+    dig = hashlib.sha256((_digest() + open(hdr).read() + open(unit).read()).encode()).hexdigest()
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return out
+    nvcc = _nvcc()
+    obj = os.path.join(ext, "mab_capi_%s.o" % name)
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", ext, "-Xptxas", "-v", "-c", unit, "-o", obj]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(obj + ".log", "w") as f:
+        f.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (unit, r.stdout[-4000:]))
+    subprocess.check_call([nvcc, "-shared", "-o", out, obj, os.path.join(OBJDIR, "mab_runtime.o"), os.path.join(OBJDIR, "mab_jit.o"),
+                           "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
+    with open(stamp, "w") as f:
+        f.write(dig)
+    if verbose:
+        print("built", out)
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--prime" in sys.argv:
+        spec = sys.argv[sys.argv.index("--prime") + 1]
+        nm, _, ex = spec.partition("=")
+        build_extra(nm, ex or None, force="--force" in sys.argv)
+    else:
+        build(force="--force" in sys.argv)

@@ -25,9 +25,11 @@ def _ptr(t):
 
 class Field:
     def __init__(self, prime: str, device=None):
-        if prime not in _lib.PRIMES:
-            raise ValueError("unsupported modulus %r (have %s)" % (prime, ", ".join(_lib.PRIMES)))
-        self.lib = _lib.load()
+        import os
+        if prime not in _lib.PRIMES and not os.path.exists(_lib.extra_lib_path(prime)):
+            raise ValueError("unsupported modulus %r (built in: %s; any other one after `python -m modarith_b200.build "
+                             "--prime %s[=<expression>]`)" % (prime, ", ".join(_lib.PRIMES), prime))
+        self.lib = _lib.load_for(prime)
         if not torch.cuda.is_available():
             raise _lib.MabError("modarith_b200 needs a CUDA device: there is no CPU fallback")
         self.prime = prime
@@ -53,7 +55,7 @@ class Field:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         fn = getattr(self.lib, "mab_%s_%s" % (self.prime, name))
         with torch.cuda.device(self.device):
-            _lib.check(fn(*lead, n, max(stride, n), stream), "mab_%s_%s" % (self.prime, name))
+            _lib.check(fn(*lead, n, max(stride, n), stream), "mab_%s_%s" % (self.prime, name), self.lib)
 
     def _chk(self, *ts):
         ref = None
@@ -238,7 +240,7 @@ class Field:
     def modprog_cubin(cls, prime, code, nin, out_regs):
         """The sm_100a cubin mab_<P>_modprog_jit compiles for this program (bytes).  Needs NVRTC, no device."""
         import ctypes
-        lib = _lib.load()
+        lib = _lib.load_for(prime)
         arr = cls._encode_program(code, out_regs)
         if not (0 <= nin <= _lib.PROG_NREG):
             raise ValueError("at most %d inputs" % _lib.PROG_NREG)
@@ -252,7 +254,7 @@ class Field:
             if rc != 0 and size.value > cap:          # the cubin is larger than the buffer: its size came back
                 cap = size.value
                 continue
-            _lib.check(rc, "mab_%s_modprog_cubin" % prime)
+            _lib.check(rc, "mab_%s_modprog_cubin" % prime, lib)
             return buf.raw[:size.value]
 
     def modprog(self, code, inputs, out_regs, outputs=None, jit=False):
@@ -291,7 +293,7 @@ class Field:
         name = "mab_%s_modprog%s" % (self.prime, "_jit" if jit else "")
         with torch.cuda.device(self.device):
             _lib.check(getattr(self.lib, name)(arr, len(code), ins_p, len(inputs), out_p, regs_p, len(outputs), n,
-                                               max(stride, n), stream), name)
+                                               max(stride, n), stream), name, self.lib)
         return outputs
 
     # -- conveniences for tests / small batches ------------------------------------------------

@@ -77,6 +77,50 @@ class MabError(RuntimeError):
     pass
 
 
+def _bind_field(lib, P):
+    """argtypes / restype of every mab_<P>_* field entry point (include/modarith_b200.h, MAB_DECLARE_FIELD)."""
+    for name, lead in FIELD_SIGNATURES.items():
+        fn = getattr(lib, "mab_%s_%s" % (P, name))
+        fn.argtypes = lead + ([] if name == "info" else _TAIL)
+        fn.restype = c_int
+    for name in ("modprog", "modprog_jit"):
+        fn = getattr(lib, "mab_%s_%s" % (P, name))
+        fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
+                       c_int, c_size_t, c_size_t, c_void_p]
+        fn.restype = c_int
+    fn = getattr(lib, "mab_%s_modprog_cubin" % P)
+    fn.argtypes = [POINTER(mab_insn), c_size_t, c_int, POINTER(ctypes.c_ubyte), c_int, c_void_p, POINTER(c_size_t)]
+    fn.restype = c_int
+
+
+_extra = {}
+
+
+def extra_lib_path(prime: str) -> str:
+    return os.path.join(PKG, "libmodarith_b200_%s.so" % prime)
+
+
+def load_for(prime: str) -> ctypes.CDLL:
+    """The library that holds mab_<prime>_*: the shipped one for the built-in moduli, otherwise the add-on library
+    `python -m modarith_b200.build --prime <prime>` produced.  Fails loudly when neither exists."""
+    if prime in PRIMES:
+        return load()
+    if prime in _extra:
+        return _extra[prime]
+    path = extra_lib_path(prime)
+    if not os.path.exists(path):
+        raise MabError("no library for modulus %r: the built-in ones are %s; build an add-on library with "
+                       "`python -m modarith_b200.build --prime %s` (or --prime %s=<expression>)"
+                       % (prime, ", ".join(PRIMES), prime, prime))
+    lib = ctypes.CDLL(path)
+    lib.mab_error_string.restype = c_char_p
+    lib.mab_error_string.argtypes = [c_int]
+    lib.mab_jit_log.restype = c_char_p
+    _bind_field(lib, prime)
+    _extra[prime] = lib
+    return lib
+
+
 def load() -> ctypes.CDLL:
     """Load the CUDA library, binding every symbol the header declares.  Fails loudly."""
     global _lib
@@ -98,22 +142,7 @@ def load() -> ctypes.CDLL:
                                    POINTER(c_int), c_void_p]
     lib.mab_probe_unsat29_modmul.argtypes = [_P, _P, _P, c_uint, c_size_t, c_size_t, c_void_p]
     for P in PRIMES:
-        for name, lead in FIELD_SIGNATURES.items():
-            fn = getattr(lib, "mab_%s_%s" % (P, name))
-            fn.argtypes = lead + ([] if name == "info" else _TAIL)
-            fn.restype = c_int
-    for P in PRIMES:
-        fn = getattr(lib, "mab_%s_modprog" % P)
-        fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
-                       c_int, c_size_t, c_size_t, c_void_p]
-        fn.restype = c_int
-        fn = getattr(lib, "mab_%s_modprog_jit" % P)
-        fn.argtypes = [POINTER(mab_insn), c_size_t, POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(ctypes.c_ubyte),
-                       c_int, c_size_t, c_size_t, c_void_p]
-        fn.restype = c_int
-        fn = getattr(lib, "mab_%s_modprog_cubin" % P)
-        fn.argtypes = [POINTER(mab_insn), c_size_t, c_int, POINTER(ctypes.c_ubyte), c_int, c_void_p, POINTER(c_size_t)]
-        fn.restype = c_int
+        _bind_field(lib, P)
     lib.mab_jit_log.restype = c_char_p
     lib.mab_NIST256_ecnmul.argtypes = [_P, _P, _P, _P, _P, c_size_t, c_void_p]
     lib.mab_NIST256_ecnmul.restype = c_int
@@ -154,16 +183,17 @@ def exported_symbols():
     return syms
 
 
-def check(code: int, what: str = ""):
+def check(code: int, what: str = "", lib=None):
     if code != 0:
-        msg = load().mab_error_string(code).decode()
+        lib = lib or load()
+        msg = lib.mab_error_string(code).decode()
         if code in (ERR_NOJIT, ERR_JIT):
-            msg += "\n" + load().mab_jit_log().decode(errors="replace")[-4000:]
+            msg += "\n" + lib.mab_jit_log().decode(errors="replace")[-4000:]
         raise MabError("%s failed: %s (code %d)" % (what or "modarith_b200 call", msg, code))
 
 
 def params(prime: str):
-    lib = load()
+    lib = load_for(prime)
     v = [c_int() for _ in range(8)]
     check(getattr(lib, "mab_%s_info" % prime)(*[ctypes.byref(x) for x in v]), "mab_%s_info" % prime)
     d = dict(zip(("nlimbs", "nbits", "nbytes", "pm1d2", "pro_sqr", "pro_mul", "montgomery", "has_curve"),

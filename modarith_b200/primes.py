@@ -85,3 +85,35 @@ SECP256K1 = Prime("SECP256K1", 2**256 - 2**32 - 977, "monty")
 NIST256ORDER = Prime("NIST256ORDER", 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551, "monty")
 EXTRA_PRIMES = {q.name: q for q in (SECP256K1, NIST256ORDER)}
 ALL_PRIMES = dict(PRIMES, **EXTRA_PRIMES)
+
+# Every other named modulus of the reference's tables (pseudo.py:1487-1550 "pseudo", monty.py:1961-2108 "monty"),
+# as data: none of them is compiled into the shipped library, `python -m modarith_b200.build --prime NAME` builds an
+# add-on library for one (libmodarith_b200_<NAME>.so, same C ABI; Field(NAME) finds it).  A name both generators
+# know is listed under the family whose plan the sm_100a generator ends up choosing anyway (make_plan tries the
+# plans in order of cost whatever the family says).
+REFERENCE_PRIMES = {
+    "PM266": ("2**266-3", "pseudo"), "NUMS256W": ("2**256-189", "pseudo"), "NUMS256E": ("2**256-189", "pseudo"),
+    "NIST521": ("2**521-1", "pseudo"), "ED521": ("2**521-1", "pseudo"), "ED25519": ("2**255-19", "pseudo"),
+    "C2065": ("2**206-5", "pseudo"), "PM336": ("2**336-3", "pseudo"), "PM383": ("2**383-187", "pseudo"),
+    "C41417": ("2**414-17", "pseudo"), "PM512": ("2**512-569", "pseudo"),
+    "NIST384": ("2**384-2**128-2**96+2**32-1", "monty"), "ED448": ("2**448-2**224-1", "monty"),
+    "GM270": ("2**270-2**162-1", "monty"), "GM240": ("2**240-2**183-1", "monty"), "GM360": ("2**360-2**171-1", "monty"),
+    "GM480": ("2**480-2**240-1", "monty"), "GM378": ("2**378-2**324-1", "monty"), "GM384": ("2**384-2**186-1", "monty"),
+    "GM512": ("2**512-2**127-1", "monty"), "NIST224": ("2**224-2**96+1", "monty"),
+    "TWEEDLE": ("0x40000000000000000000000000000000038aa127696286c9842cafd400000001", "monty"),
+    "SIDH434": ("2**216*3**137-1", "monty"), "SIDH503": ("2**250*3**159-1", "monty"), "SIDH610": ("2**305*3**192-1", "monty"),
+    "SIDH751": ("2**372*3**239-1", "monty"), "MFP4": ("3*67*(2**246)-1", "monty"),
+    "MFP7": ("2**145*(3**9)*(59**3)*(311**3)*(317**3)*(503**3)-1", "monty"),
+    "MFP1973": ("0x34e29e286b95d98c33a6a86587407437252c9e49355147ffffffffffffffffff", "monty"),
+    "ED248": ("5*2**248-1", "monty"),
+}
+
+
+def named(name: str) -> Prime:
+    """A modulus by the reference's name: one of the built-in ones, or a table entry above."""
+    if name in ALL_PRIMES:
+        return ALL_PRIMES[name]
+    if name in REFERENCE_PRIMES:
+        expr, family = REFERENCE_PRIMES[name]
+        return Prime(name, eval(expr, {"__builtins__": {}}), family)
+    raise KeyError(name)

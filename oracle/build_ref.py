@@ -53,6 +53,9 @@ TARGETS = [
     # monty.py:2110-2127); they back the vectors for the generator's full-Montgomery fall-back plan
     ("SECP256K1", "monty.py", "SECP256K1", True, False),
     ("NIST256ORDER", "monty.py", "00115792089210356248762697446949407573529996955224135760342422259061068512044369", True, False),
+    # a modulus that is NOT compiled into the shipped library: backs the test of the add-on build
+    # (python -m modarith_b200.build --prime NIST384; monty.py named table)
+    ("NIST384", "monty.py", "NIST384", True, False),
 ]
 
 
