@@ -231,6 +231,17 @@ MAB_API int mab_ED25519_ecnmul2(const char *e, const char *x1, const char *y1, c
                                 char *xo, char *yo, size_t n, void *stream);
 
 /* ---- RFC 7748 (rfc7748.c:156  void rfc7748(const char *bk, const char *bu, char *bv)) ---- */
+/* The ladder entry points of one Montgomery curve, described one by one below for X25519 and X448.  An add-on
+ * library built with `python -m modarith_b200.build --prime NAME[=<expression>] --a24 N --cof K [--generator G]`
+ * exports the same set for a user-defined curve -- the counterpart of adding an A24 / COF / GENERATOR block to
+ * "Describe Montgomery Curve parameters" in rfc7748.c:117-132. */
+#define MAB_DECLARE_CURVE(P)                                                                                  \
+  MAB_API int mab_##P##_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);            \
+  MAB_API int mab_##P##_rfc7748_perkey(const char *bk, const char *bu, char *bv, size_t n, void *stream);     \
+  MAB_API int mab_##P##_rfc7748_validate(const char *bk, const char *bu, char *bv, size_t n, void *stream);   \
+  MAB_API int mab_##P##_rfc7748_host(const char *bk, const char *bu, char *bv, size_t n, int device);         \
+  MAB_API int mab_##P##_rfc7748_host_multi(const char *bk, const char *bu, char *bv, size_t n, int ndev);
+
 /* bv[i] = clamp(bk[i]) * bu[i]; little-endian Nbytes strings, n keys, device pointers. */
 MAB_API int mab_X25519_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);
 MAB_API int mab_X448_rfc7748(const char *bk, const char *bu, char *bv, size_t n, void *stream);

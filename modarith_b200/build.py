@@ -7,6 +7,7 @@ The reference's build step is "run the generator, compile what it printed"
     python -m modarith_b200.build --force
     python -m modarith_b200.build --prime NIST384            # add-on library for another modulus of the reference's
     python -m modarith_b200.build --prime MYP="2**414-17"    # tables, or for any prime given as an expression
+    python -m modarith_b200.build --prime M383="2**383-187" --a24 516287 --cof 3 --generator 12   # with its ladder
 """
 from __future__ import annotations
 
@@ -117,12 +118,15 @@ def extra_lib_path(name):
     return os.path.join(PKG, "libmodarith_b200_%s.so" % name)
 
 
-def build_extra(name, expr=None, force=False, verbose=True):
+def build_extra(name, expr=None, force=False, verbose=True, curve=None):
     """An add-on library with the field entry points (mab_<NAME>_modmul, ..., _modprog, _modprog_jit) for a modulus
     that is not one of the five built in: the reference's `python3 monty.py 64 NIST384` + compile, in one step
     (pseudo.py:1694-1702).  Same C ABI, same kernels (csrc/mab_capi.inc instantiated on the generated header), linked
     with the library's own runtime objects so that it stands alone: modarith_b200/libmodarith_b200_<NAME>.so, which
-    Field(NAME) loads.  `expr`: a Python integer expression for a modulus the tables do not name."""
+    Field(NAME) loads.  `expr`: a Python integer expression for a modulus the tables do not name.
+    `curve` = (a24, cof, generator): the modulus carries a Montgomery curve B y^2 = x^3 + A x^2 + x with
+    a24 = (A - 2) / 4 and cofactor 2^cof -- the constants a user adds to rfc7748.c:117-132 for a curve of their own --
+    and the library also exports the ladder entry points mab_<NAME>_rfc7748[_perkey|_validate|_host|_host_multi]."""
     import re
     from .gen.cli import generate
     from .primes import Prime, named
@@ -133,6 +137,11 @@ def build_extra(name, expr=None, force=False, verbose=True):
         P = Prime(name, int(p), "monty")
     else:
         P = named(name)
+    if curve is not None:
+        a24, cof, gen = (int(v) for v in curve)
+        if not (0 < a24 < 2**31 and cof in (2, 3) and 0 < gen < 2**31):
+            raise ValueError("curve constants: 0 < a24 < 2^31, cof 2 or 3 (rfc7748.c:121-131), 0 < generator < 2^31")
+        P = Prime(P.name, P.p, P.family, a24=a24, cof=cof, generator=gen)
     build(verbose=False)                                   # the runtime objects and the common JIT sources
     ext = os.path.join(OBJDIR, "ext")
     os.makedirs(ext, exist_ok=True)
@@ -140,9 +149,10 @@ def build_extra(name, expr=None, force=False, verbose=True):
     generate(P, hdr, verbose=False)
     unit = os.path.join(ext, "mab_capi_%s.cu" % name)
     _write_if_changed(unit, '// C ABI instantiation for %s (python -m modarith_b200.build --prime)\n#include "field_%s.cuh"\n'
-                      '#include "modarith_b200.h"\nextern "C" {\nMAB_DECLARE_FIELD(%s)      // exported like the built-in moduli\n}\n'
-                      '#define MAB_P %s\n#define MAB_F F_%s\n#define MAB_JIT_SRC "jit_src_%s.inc"\n#include "mab_capi.inc"\n'
-                      % (name, name, name, name, name, name))
+                      '#include "modarith_b200.h"\nextern "C" {\nMAB_DECLARE_FIELD(%s)      // exported like the built-in moduli\n%s}\n'
+                      '#define MAB_P %s\n#define MAB_F F_%s\n%s#define MAB_JIT_SRC "jit_src_%s.inc"\n#include "mab_capi.inc"\n'
+                      % (name, name, name, "MAB_DECLARE_CURVE(%s)\n" % name if curve else "", name, name,
+                         "#define MAB_HAS_CURVE 1\n" if curve else "", name))
     _write_if_changed(os.path.join(ext, "jit_src_%s.inc" % name), _as_literal("kJitSrc_field", open(hdr).read()))
     out = extra_lib_path(name)
     stamp = os.path.join(ext, "digest_%s.txt" % name)
@@ -170,6 +180,12 @@ if __name__ == "__main__":
     if "--prime" in sys.argv:
         spec = sys.argv[sys.argv.index("--prime") + 1]
         nm, _, ex = spec.partition("=")
-        build_extra(nm, ex or None, force="--force" in sys.argv)
+
+        def opt(flag, default=None):
+            return sys.argv[sys.argv.index(flag) + 1] if flag in sys.argv else default
+        cv = None
+        if "--a24" in sys.argv:
+            cv = (int(opt("--a24")), int(opt("--cof", "3")), int(opt("--generator", "9")))
+        build_extra(nm, ex or None, force="--force" in sys.argv, curve=cv)
     else:
         build(force="--force" in sys.argv)

@@ -93,6 +93,18 @@ def _bind_field(lib, P):
     fn.restype = c_int
 
 
+def _bind_curve(lib, P):
+    """The ladder entry points of one curve (include/modarith_b200.h, MAB_DECLARE_CURVE)."""
+    for name in ("rfc7748", "rfc7748_perkey", "rfc7748_validate"):
+        fn = getattr(lib, "mab_%s_%s" % (P, name))
+        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
+        fn.restype = c_int
+    for name in ("rfc7748_host", "rfc7748_host_multi"):
+        fn = getattr(lib, "mab_%s_%s" % (P, name))
+        fn.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int]
+        fn.restype = c_int
+
+
 _extra = {}
 
 
@@ -117,6 +129,8 @@ def load_for(prime: str) -> ctypes.CDLL:
     lib.mab_error_string.argtypes = [c_int]
     lib.mab_jit_log.restype = c_char_p
     _bind_field(lib, prime)
+    if hasattr(lib, "mab_%s_rfc7748" % prime):              # built with a Montgomery curve (--a24 / --cof)
+        _bind_curve(lib, prime)
     _extra[prime] = lib
     return lib
 
@@ -153,19 +167,7 @@ def load() -> ctypes.CDLL:
         fn.argtypes = [_P] * 8 + [c_size_t, c_void_p]
         fn.restype = c_int
     for P in CURVES:
-        fn = getattr(lib, "mab_%s_rfc7748" % P)
-        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
-        fn.restype = c_int
-        fn = getattr(lib, "mab_%s_rfc7748_perkey" % P)
-        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
-        fn.restype = c_int
-        fn = getattr(lib, "mab_%s_rfc7748_validate" % P)
-        fn.argtypes = [_P, _P, _P, c_size_t, c_void_p]
-        fn.restype = c_int
-        for name in ("mab_%s_rfc7748_host" % P, "mab_%s_rfc7748_host_multi" % P):
-            fn = getattr(lib, name)
-            fn.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_int]
-            fn.restype = c_int
+        _bind_curve(lib, P)
     _lib = lib
     return lib
 

@@ -71,10 +71,20 @@ def rfc7748(curve: str, bk, bu, bv=None, device=None, validate=False):
     all zero when bu is not on the curve (device tensors only).
     Host arrays: device = an index (default: the current device), or "all" / a count >= 2 given as
     ("all", count) to spread the batch over the GPUs of the box."""
-    if curve not in _NBYTES:
-        raise ValueError("unsupported curve %r (have %s)" % (curve, ", ".join(_NBYTES)))
-    lib = _lib.load()
-    nb = _NBYTES[curve]
+    if curve in _NBYTES:
+        lib, nb = _lib.load(), _NBYTES[curve]
+    else:
+        # a user-defined Montgomery curve: an add-on library built with its constants
+        # (python -m modarith_b200.build --prime NAME[=<expression>] --a24 N --cof K [--generator G])
+        import os
+        if not os.path.exists(_lib.extra_lib_path(curve)):
+            raise ValueError("unsupported curve %r (built in: %s; a curve of your own after `python -m modarith_b200.build "
+                             "--prime %s=<modulus> --a24 <(A-2)/4> --cof <2|3>`)" % (curve, ", ".join(_NBYTES), curve))
+        lib = _lib.load_for(curve)
+        par = _lib.params(curve)
+        if not par["has_curve"]:
+            raise ValueError("the add-on library for %r was built without curve constants (--a24 / --cof)" % curve)
+        nb = par["nbytes"]
     if isinstance(bk, torch.Tensor) and bk.is_cuda:
         _check_dev("bk", bk, nb)
         _check_dev("bu", bu, nb, bk)
@@ -85,7 +95,7 @@ def rfc7748(curve: str, bk, bu, bv=None, device=None, validate=False):
         stream = torch.cuda.current_stream(bk.device).cuda_stream
         with torch.cuda.device(bk.device):
             name = "mab_%s_rfc7748%s" % (curve, "_validate" if validate else "")
-            _lib.check(getattr(lib, name)(bk.data_ptr(), bu.data_ptr(), bv.data_ptr(), bk.shape[0], stream), name)
+            _lib.check(getattr(lib, name)(bk.data_ptr(), bu.data_ptr(), bv.data_ptr(), bk.shape[0], stream), name, lib)
         return bv
     if validate:
         raise ValueError("validate=True is available for device tensors only")
@@ -112,11 +122,11 @@ def rfc7748(curve: str, bk, bu, bv=None, device=None, validate=False):
         raise _lib.MabError("modarith_b200 needs a CUDA device: there is no CPU fallback")
     if multi is not None:
         name = "mab_%s_rfc7748_host_multi" % curve
-        _lib.check(getattr(lib, name)(kp, up, vp, ks[0], multi), name)
+        _lib.check(getattr(lib, name)(kp, up, vp, ks[0], multi), name, lib)
     else:
         dev = torch.cuda.current_device() if device is None else int(device)
         name = "mab_%s_rfc7748_host" % curve
-        _lib.check(getattr(lib, name)(kp, up, vp, ks[0], dev), name)
+        _lib.check(getattr(lib, name)(kp, up, vp, ks[0], dev), name, lib)
     del k, u, v
     return bv
 

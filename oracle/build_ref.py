@@ -57,6 +57,13 @@ TARGETS = [
     # (python -m modarith_b200.build --prime NIST384; monty.py named table)
     ("NIST384", "monty.py", "NIST384", True, False),
 ]
+# a user-defined Montgomery curve (y^2 = x^3 + 2065150 x^2 + x over 2^383 - 187, a24 = (A - 2) / 4, cofactor 8, base
+# point u = 12): backs the test of an add-on library WITH a ladder (python -m modarith_b200.build --prime M383=... --a24 ...)
+M383 = (516287, 3, 12)
+CURVE_TARGETS = [
+    ("M383", "pseudo.py", "PM383", False, True, M383),
+    ("M383_validate", "pseudo.py", "PM383", True, True, M383),
+]
 
 
 def _patch_settings(text, generic):
@@ -70,7 +77,9 @@ def _patch_settings(text, generic):
     return text
 
 
-def build_one(name, script, prime, generic, ladder, cflags):
+def build_one(name, script, prime, generic, ladder, cflags, curve=None):
+    """curve = (a24, cof, generator): a user-defined Montgomery curve -- its constants are added to the "Describe
+    Montgomery Curve parameters" section of rfc7748.c exactly as its comment asks the user to (rfc7748.c:117-132)."""
     work = tempfile.mkdtemp(prefix="mab_ref_%s_" % name)
     try:
         bindir = os.path.join(work, "bin")
@@ -98,8 +107,13 @@ def build_one(name, script, prime, generic, ladder, cflags):
             with open(os.path.join(REF, "rfc7748.c")) as f:
                 drv = f.read()
             drv = drv.replace("#define COUNT_CLOCKS", "//#define COUNT_CLOCKS", 1)
+            if curve is not None:
+                anchor = "// Describe Montgomery Curve parameters"
+                assert drv.count(anchor) == 1
+                drv = drv.replace(anchor, anchor + "\n#define A24 %d\n#define COF %d\n#define GENERATOR %d\n#define TWIST_SECURE\n"
+                                  % tuple(curve))
             if name.endswith("_validate"):
-                assert drv.count("#define TWIST_SECURE") == 2
+                assert drv.count("#define TWIST_SECURE") == (3 if curve is not None else 2)
                 drv = drv.replace("#define TWIST_SECURE", "//#define TWIST_SECURE")
             marker = "/*** Insert automatically generated code for modulus field.c here ***/"
             assert marker in drv
@@ -183,6 +197,8 @@ def main():
     for t in TARGETS:
         so = build_one(*t, cflags)
         print("built", so)
+    for t in CURVE_TARGETS:
+        print("built", build_one(*t[:5], cflags, curve=t[5]))
     print("built", build_curve(cflags, "NIST256", "weierstrass.c"))
     print("built", build_curve(cflags, "ED25519", "edwards.c"))
     return 0

@@ -62,3 +62,54 @@ def test_every_named_modulus_of_the_reference_has_a_plan():
         assert pow(3, P.p - 1, P.p) == 1, name                 # the reference's own sanity check, pseudo.py:1561-1564
         plan = make_plan(P)
         assert plan.L == (P.nbits + 31) // 32, name
+
+
+# ---- an add-on library WITH a ladder: a user-defined Montgomery curve ------------------------------------------------
+M383_P = 2**383 - 187
+M383_CURVE = (516287, 3, 12)          # a24 = (A - 2) / 4 for A = 2065150, cofactor 2^3, base point u = 12
+
+
+@pytest.fixture(scope="module")
+def m383():
+    from modarith_b200 import build
+    return build.build_extra("M383", "2**383-187", verbose=False, curve=M383_CURVE)
+
+
+def test_curve_addon_exports_the_ladder_abi(m383):
+    from modarith_b200 import lib as mlib
+    dll = ctypes.CDLL(m383)
+    for n in ("rfc7748", "rfc7748_perkey", "rfc7748_validate", "rfc7748_host", "rfc7748_host_multi", "modmul", "modprog_jit"):
+        assert hasattr(dll, "mab_M383_" + n), n
+    par = mlib.params("M383")
+    assert (par["nlimbs"], par["nbits"], par["nbytes"], par["has_curve"], par["pm1d2"]) == (12, 383, 48, 1, 2)
+    from modarith_b200 import build
+    with pytest.raises(ValueError):
+        build.build_extra("BADCURVE", "2**383-187", curve=(516287, 5, 12))      # cofactor 2^2 or 2^3 only
+
+
+def test_oracle_ladder_on_the_user_curve_matches_the_reference_build():
+    """Pins the oracle for this curve: the reference's rfc7748.c with the curve's constants added to its "Describe
+    Montgomery Curve parameters" section (oracle/build_ref.py), against the restatement, on random raw keys."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    from field_oracle import rfc7748 as oracle_rfc7748
+    from oracle_primes import OraclePrime
+    sys.path.insert(0, os.path.dirname(__file__))
+    import util
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_M383.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    ref = ctypes.CDLL(path)
+    P = OraclePrime("M383", M383_P, a24=M383_CURVE[0], cof=M383_CURVE[1], generator=M383_CURVE[2])
+    k, u = util.random_bytes(3831, 24, 48), util.random_bytes(3832, 24, 48)
+    u[0] = 0
+    u[1] = np.frombuffer((12).to_bytes(48, "little"), dtype=np.uint8)
+    u[2] = np.frombuffer((M383_P - 1).to_bytes(48, "little"), dtype=np.uint8)
+    k[3] = 255
+    want = util.ref_rfc7748_batch(ref, k, u)
+    for i in range(24):
+        assert oracle_rfc7748(P, k[i].tobytes(), u[i].tobytes()) == want[i].tobytes(), i
+    vref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_M383_validate.so"))
+    wantv = util.ref_rfc7748_batch(vref, k, u)
+    for i in range(24):
+        assert oracle_rfc7748(P, k[i].tobytes(), u[i].tobytes(), twist_secure=False) == wantv[i].tobytes(), i

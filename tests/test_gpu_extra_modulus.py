@@ -75,3 +75,60 @@ def test_api_vs_oracle_and_programs(F):
     for jit in (False, True):
         (res,) = F.modprog(code, [x, y], [6], jit=jit)
         assert F.to_ints(res) == want, jit
+
+
+# ---- a user-defined Montgomery curve: the add-on library's ladder ------------------------------------------------------
+M383_P = 2**383 - 187
+
+
+def _ref(name):
+    import ctypes
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_%s.so" % name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    return ctypes.CDLL(path)
+
+
+def _m383_batch(n):
+    k, u = util.random_bytes(38301, n, 48), util.random_bytes(38302, n, 48)
+    rows = [0, 1, 12, M383_P - 1, M383_P, M383_P + 1, (1 << 383) - 1, (1 << 384) - 1]
+    for i, v in enumerate(rows):
+        u[i] = np.frombuffer(v.to_bytes(48, "little"), dtype=np.uint8)
+    k[len(rows)] = 0
+    k[len(rows) + 1] = 255
+    return k, u
+
+
+def test_user_curve_ladder_vs_reference_build():
+    from modarith_b200 import lib as mlib
+    from modarith_b200.rfc7748 import rfc7748
+    if not os.path.exists(mlib.extra_lib_path("M383")):
+        pytest.fail("libmodarith_b200_M383.so is missing: __graft_entry__.build() builds it")
+    n = (1 << 14) + 77                      # more than one chunk round of the persistent grid's queues, ragged
+    k, u = _m383_batch(n)
+    want = util.ref_rfc7748_batch(_ref("M383"), k, u)
+    dk, du = torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda()
+    got = rfc7748("M383", dk, du)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # one key per thread, one inversion per key: same bytes
+    lib = mlib.load_for("M383")
+    out = torch.empty_like(dk)
+    mlib.check(lib.mab_M383_rfc7748_perkey(dk.data_ptr(), du.data_ptr(), out.data_ptr(), n,
+                                           torch.cuda.current_stream().cuda_stream), "perkey", lib)
+    assert np.array_equal(out.cpu().numpy(), want)
+    # host buffers: pageable (staged) and pinned (zero-copy)
+    assert np.array_equal(rfc7748("M383", k, u), want)
+    pk, pu = torch.from_numpy(k).pin_memory(), torch.from_numpy(u).pin_memory()
+    assert np.array_equal(rfc7748("M383", pk, pu).numpy(), want)
+
+
+def test_user_curve_point_validation_vs_reference_build():
+    """The driver without TWIST_SECURE (rfc7748.c:228-251) -- what a user-defined curve that is not twist secure runs."""
+    from modarith_b200.rfc7748 import rfc7748
+    n = 1 << 12
+    k, u = _m383_batch(n)
+    want = util.ref_rfc7748_batch(_ref("M383_validate"), k, u)
+    got = rfc7748("M383", torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda(), validate=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    zero = (want == 0).all(axis=1).sum()
+    assert n // 4 < zero < 3 * n // 4         # about half of all u are x-coordinates of points on the twist

@@ -65,5 +65,19 @@ F = Field("NIST256")
 x, _ = F.modimp(torch.randint(0, 256, (333, 32), dtype=torch.uint8, device="cuda", generator=g))
 y, _ = F.modimp(torch.randint(0, 256, (333, 32), dtype=torch.uint8, device="cuda", generator=g))
 F.modprog([("mul", 2, 0, 1), ("add", 3, 2, 0), ("sqr", 3, 3, 0), ("sub", 4, 3, 1), ("inv", 5, 4, 0), ("mli", 6, 5, 0, 7)], [x, y], [3, 5, 6])
+# the same program compiled at run time (NVRTC) into a kernel of its own, and on an add-on modulus
+prog = [("mul", 2, 0, 1), ("add", 3, 2, 0), ("sqr", 3, 3, 0), ("sub", 4, 3, 1), ("inv", 5, 4, 0), ("mli", 6, 5, 0, 7)]
+a = F.modprog(prog, [x, y], [3, 5, 6])
+b = F.modprog(prog, [x, y], [3, 5, 6], jit=True)
+assert all(torch.equal(p, q) for p, q in zip(a, b))
+import os
+from modarith_b200 import lib as mlib
+if os.path.exists(mlib.extra_lib_path("NIST384")):
+    F3 = Field("NIST384")
+    x3, _ = F3.modimp(torch.randint(0, 256, (517, 48), dtype=torch.uint8, device="cuda", generator=g))
+    r3 = F3.alloc(517)
+    F3.modmul(x3, x3, r3)
+    F3.modinv(r3, None, r3)
+    F3.modprog([("sqr", 1, 0, 0), ("sub", 1, 1, 0)], [x3], [1], jit=True)
 torch.cuda.synchronize()
 print("sanitize smoke done")
