@@ -676,6 +676,198 @@ class PseudoMersenne33(Plan):
         return asm
 
 
+class PseudoMersenneBits(Plan):
+    """2^n - c for ANY n (xs = 32L - n >= 2 spare bits in the top word, L even or odd) and c < 2^15 -- what
+    pseudo.py's named table mostly holds (2^266 - 3, 2^206 - 5, 2^336 - 3, 2^414 - 17, 2^521 - 1; pseudo.py:1487-1550)
+    and the word-aligned plan above cannot take.  Plain residues; stored values are any representative below
+    2^n + 2^32.  Everything is folded at bit n: the part of a value at or above bit n is extracted with funnel
+    shifts, multiplied by c and added at the bottom (second_pass, pseudo.py:557-611, restated for saturated limbs).
+
+        mul / sqr   T = a*b < 2^(2n+1)          H = T >> n  (L funnel shifts),  R = (T mod 2^n) + c*H  (L wide
+                    multiplies on even / odd windows, one merge),  then the few bits of R at or above bit n once more
+        add / sub   one chain (sub: 2p added back under the borrow mask), then the top bits once
+
+    L^2 + L wide multiplies per modmul where the fall-back plan needs 2 L^2 + L."""
+    family = "pseudo"
+
+    def __init__(self, prime):
+        super().__init__(prime)
+        n, L = prime.nbits, self.L
+        self.c = (1 << n) - prime.p
+        self.xs = 32 * L - n
+        assert 2 <= self.xs <= 31 and L >= 3, "needs two spare bits in the top word"
+        assert 0 < self.c < (1 << 15), "not of the form 2^n - c with a small c"
+        self.bound = (1 << n) + (1 << 32)
+        self.mask = M32 >> self.xs                      # bits of the top word below bit n
+
+    # -- pieces -----------------------------------------------------------------------------------
+    def _fold_top(self, asm, r, top=0, wide=False):
+        """r (L words) + top * 2^(32L)  ->  L words below 2^n + c*h: everything at or above bit n (h, which must
+        fit a word) times c, added at the bottom.  wide=True when c*h may exceed 32 bits (raw imports)."""
+        L, xs = self.L, self.xs
+        h = asm.tmp()
+        if isinstance(top, int) and top == 0:
+            asm.shr(h, r[L - 1], 32 - xs)
+        else:
+            asm.shfl(h, r[L - 1], top, xs)
+        last = asm.tmp()
+        asm.logic("and", last, r[L - 1], self.mask)
+        o = asm.tmp(L)
+        asm.madlo(o[0], h, self.c, r[0], cout=True)
+        start = 1
+        if wide:
+            asm.madhi(o[1], h, self.c, r[1], cin=True, cout=True)
+            start = 2
+        for k in range(start, L - 1):
+            asm.add(o[k], r[k], 0, cin=True, cout=True)
+        asm.add(o[L - 1], last, 0, cin=True)
+        return o, h
+
+    def _fold_words(self, asm, v):
+        """v: more than L words (a product: 2L, or L+1 after a small multiplication), value < 2^(2n+1)  ->  L words
+        below 2^n + 2^32."""
+        L, xs, c = self.L, self.xs, self.c
+        nv = len(v)
+        assert L < nv <= 2 * L
+        # H = v >> n, word k = high word of (v[L+k] : v[L-1+k]) << xs
+        m = nv - L + 1 if nv < 2 * L else L              # a full product is below 2^(2n+1): H has L words
+        H = []
+        for k in range(m):
+            lo = v[L - 1 + k]
+            hi = v[L + k] if L + k < nv else 0
+            d = asm.tmp()
+            if isinstance(hi, int) and hi == 0:
+                asm.shr(d, lo, 32 - xs)
+            else:
+                asm.shfl(d, lo, hi, xs)
+            H.append(d)
+        last = asm.tmp()
+        asm.logic("and", last, v[L - 1], self.mask)
+        if m <= 2:
+            # after a small multiplication: H is below 2^33, c*H below 2^48 -- one wide multiply, one add chain
+            p0, p1 = asm.tmp(), asm.tmp()
+            asm.mullo(p0, H[0], c)
+            asm.mulhi(p1, H[0], c)
+            if m == 2:
+                q = asm.tmp()
+                asm.madlo(q, H[1], c, p1)                  # H[1] is 0 or 1 and p1 < c: cannot carry
+                p1 = q
+            s = asm.tmp(L)
+            asm.add_chain(s, list(v[:L - 1]) + [last], [p0, p1] + [0] * (L - 2))     # < 2^n + 2^48: no carry out
+            r, _ = self._fold_top(asm, s)
+            return r
+        lo = list(v[:L - 1]) + [last] + [0, 0]
+        # R = lo + c*H over L+1 words: even words of H chain onto the even-aligned windows of lo, odd words are
+        # independent wide multiplies on the odd-aligned windows, one add-with-carry chain merges the two
+        t = {}
+        ev = []
+        for k in range(0, m, 2):
+            t[k], t[k + 1] = asm.tmp(), asm.tmp()
+            ev.append((t[k], t[k + 1], H[k], c, lo[k], lo[k + 1]))
+        ke = 2 * len(ev)                                   # first word above the even chain
+        if ke <= L:                                        # L even: the chain ends at word L-1, its carry is word L
+            assert ke == L
+            t[ke] = asm.tmp()
+            asm.wide_chain(ev, last_carry_to=(t[ke], 0))
+        else:
+            asm.wide_chain(ev, last_carry_to=None)         # L odd: the window (L-1, L) is the top, nothing leaves it
+        o = {}
+        for k in range(1, m, 2):
+            o[k], o[k + 1] = asm.tmp(), asm.tmp()
+            asm.mullo(o[k], H[k], c)
+            asm.mulhi(o[k + 1], H[k], c)
+        res = [t[0]]
+        started = False
+        for k in range(1, L + 1):
+            a, b = t.get(k, lo[k] if k < len(lo) else 0), o.get(k, 0)
+            if not started and isinstance(b, int) and b == 0:
+                res.append(a)
+                continue
+            d = asm.tmp()
+            asm.add(d, a, b, cin=started, cout=(k < L))
+            started = True
+            res.append(d)
+        r, _ = self._fold_top(asm, res[:L], res[L])
+        return r
+
+    def reduce_wide(self, asm, T):
+        return self._fold_words(asm, T)
+
+    def reduce_small(self, asm, T):
+        return self._fold_words(asm, T)
+
+    def build_mla(self):
+        asm = Asm(self.name + ".mla")
+        a, c = self._io(asm, ["a", "c"])
+        asm.inp("b")
+        T = satmul.times_small(asm, a, "b")               # L+1 words
+        L = self.L
+        s = asm.tmp(L + 1)
+        asm.add_chain(s, T, list(c) + [0])                 # a*b + c < 2^(n+33): still L+1 words
+        self._outs(asm, self._fold_words(asm, s))
+        return asm
+
+    def build_add(self):
+        asm = Asm(self.name + ".add")
+        a, b = self._io(asm, ["a", "b"])
+        L = self.L
+        s = asm.tmp(L)
+        asm.add_chain(s, a, b)                             # < 2^(n+1) + 2^33 < 2^(32L): no carry out
+        r, _ = self._fold_top(asm, s)
+        self._outs(asm, r)
+        return asm
+
+    def build_sub(self, neg):
+        asm = Asm(self.name + (".neg" if neg else ".sub"))
+        L = self.L
+        if neg:
+            (b,) = self._io(asm, ["b"])
+            a = [0] * L
+        else:
+            a, b = self._io(asm, ["a", "b"])
+        d = asm.tmp(L)
+        m = asm.tmp()
+        asm.sub_chain(d, a, b, borrow_to=m)                # value = d - 2^(32L)*[m]
+        # a - b > -(2^n + 2^32) > -2p: add 2p back under the borrow mask (the carry out cancels the borrow)
+        pw = words(2 * self.p, L)
+        ops = []
+        for k in range(L):
+            if pw[k] == 0:
+                ops.append(0)
+            elif pw[k] == M32:
+                ops.append(m)
+            else:
+                t = asm.tmp()
+                asm.logic("and", t, m, pw[k])
+                ops.append(t)
+        e = asm.tmp(L)
+        asm.add_chain(e, d, ops, wrap_ok=True)
+        r, _ = self._fold_top(asm, e)                       # < 2^(n+1) + 2^32: the top bits once
+        self._outs(asm, r)
+        return asm
+
+    def build_canon(self):
+        """Any L-word value (a stored one, or a raw import up to 2^(32L)) -> canonical residue; lt = 1 iff the input
+        was already < p (modfsb's return, pseudo.py:272-283)."""
+        asm = Asm(self.name + ".canon")
+        (a,) = self._io(asm, ["a"])
+        r1, h1 = self._fold_top(asm, a, wide=True)         # < 2^n + c*2^xs
+        r2, h2 = self._fold_top(asm, r1)                   # < 2^n + c = p + 2c
+        lt = asm.tmp()
+        r = self._cond_sub_p(asm, r2, want_flag=lt)
+        # the flag describes the INPUT: it was below p iff nothing was folded and the subtraction borrowed
+        nz, t, mz, nm, lt2 = asm.tmp(), asm.tmp(), asm.tmp(), asm.tmp(), asm.tmp()
+        asm.logic("or", nz, h1, h2)
+        asm.sub(t, 0, nz, cout=True)
+        asm.nocheck.add(len(asm.ins))
+        asm.sub(mz, 0, 0, cin=True)                        # all-ones iff something was folded
+        asm.not_(nm, mz)
+        asm.logic("and", lt2, lt, nm)
+        self._outs(asm, r)
+        asm.out("lt", lt2)
+        return asm
+
+
 class GenMersenne(Plan):
     """p = 2^(2h) - 2^h - 1, h = 32*H (X448: H=7, L=14).  Stored values are any
     representative < 2^(2h) (< 2p).  2^(2h) == 2^h + 1, so a double-length value
@@ -1136,6 +1328,8 @@ def make_plan(prime: Prime) -> Plan:
         cands.append(PseudoMersenne)
     if L % 2 == 0 and n == 32 * L and 0 < c - (1 << 32) < (1 << 15):
         cands.append(PseudoMersenne33)
+    if 0 < c < (1 << 15) and 32 * L - n >= 2 and os.environ.get("MAB_PMBITS", "1") != "0":
+        cands.append(PseudoMersenneBits)
     cands += [Montgomery, MontgomeryFull]
     err = None
     for cls in cands:

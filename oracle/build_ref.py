@@ -56,6 +56,10 @@ TARGETS = [
     # a modulus that is NOT compiled into the shipped library: backs the test of the add-on build
     # (python -m modarith_b200.build --prime NIST384; monty.py named table)
     ("NIST384", "monty.py", "NIST384", True, False),
+    # 2^n - c with n not a multiple of 32 (the generator's bit-level pseudo-Mersenne plan): 2^414 - 17 on 13 limbs with
+    # two spare bits, 2^521 - 1 on 17 limbs with 23 (pseudo.py named table)
+    ("C41417", "pseudo.py", "C41417", True, False),
+    ("NIST521", "pseudo.py", "NIST521", True, False),
 ]
 # a user-defined Montgomery curve (y^2 = x^3 + 2065150 x^2 + x over 2^383 - 187, a24 = (A - 2) / 4, cofactor 8, base
 # point u = 12): backs the test of an add-on library WITH a ladder (python -m modarith_b200.build --prime M383=... --a24 ...)

@@ -17,14 +17,25 @@ def built():
     return build.build(verbose=False)
 
 
+def _macro_body(h, name):
+    """Text of a multi-line #define (lines joined by backslashes)."""
+    m = re.search(r"#define %s\(P\)(.*?[^\\])\n" % name, h, re.S)
+    return m.group(1)
+
+
 def header_symbols():
     h = open(os.path.join(ROOT, "include", "modarith_b200.h")).read()
+    field = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", _macro_body(h, "MAB_DECLARE_FIELD"))
+    curve = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", _macro_body(h, "MAB_DECLARE_CURVE"))
+    assert len(field) == 36 and sorted(curve) == ["rfc7748", "rfc7748_host", "rfc7748_host_multi", "rfc7748_perkey",
+                                                  "rfc7748_validate"]
     syms = set(re.findall(r"\b(mab_[A-Za-z0-9_]+)\s*\(", h))
-    macro = re.findall(r"mab_##P##_([a-z0-9_]+)\s*\(", h)
     for P in re.findall(r"MAB_DECLARE_FIELD\((\w+)\)\n", h):
         if P != "P":
-            syms |= {"mab_%s_%s" % (P, m) for m in macro}
-    syms |= set(re.findall(r"\b(mab_X\d+_rfc7748(?:_host|_validate|_perkey)?)\s*\(", h))
+            syms |= {"mab_%s_%s" % (P, m) for m in field}
+    # the built-in curves are declared one by one (with their comments); the macro declares the same set for add-ons
+    for P in ("X25519", "X448"):
+        assert {"mab_%s_%s" % (P, m) for m in curve} <= syms
     return syms
 
 

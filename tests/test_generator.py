@@ -5,8 +5,8 @@ import random
 import pytest
 
 from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime
-from modarith_b200.gen.plan import (make_plan, PseudoMersenne, PseudoMersenne33, GenMersenne, Montgomery, MontgomeryFull,
-                                    words, value)
+from modarith_b200.gen.plan import (make_plan, PseudoMersenne, PseudoMersenne33, PseudoMersenneBits, GenMersenne, Montgomery,
+                                    MontgomeryFull, words, value)
 from modarith_b200.gen.ptx import Asm, LostCarry
 from modarith_b200.gen import satmul
 from modarith_b200.gen.emit import emit_field_header
@@ -104,3 +104,23 @@ def test_fallback_plan_accepts_any_odd_modulus():
     for nm, p in {"PM383": 2**383 - 187, "PM512": 2**512 - 569}.items():
         plan = make_plan(Prime(nm, p, "pseudo"))
         assert isinstance(plan, PseudoMersenne) and plan.self_check(trials=40, seed=7)
+
+
+@pytest.mark.parametrize("nm,expr", [("C41417", "2**414-17"), ("NIST521", "2**521-1"), ("PM266", "2**266-3"),
+                                     ("C2065", "2**206-5"), ("PM336", "2**336-3"), ("M221", "2**221-3")])
+def test_bit_level_pseudo_mersenne_plan(nm, expr):
+    """2^n - c with n not a multiple of 32 and any limb count (most of pseudo.py's named table, pseudo.py:1487-1550):
+    folded at bit n, L^2 + L wide multiplies per modmul where the fall-back plan needs 2 L^2 + L.  Stored values stay
+    below 2^n + 2^32; canon covers raw imports up to 2^(32L) (checked by self_check over that whole range)."""
+    p = eval(expr)
+    plan = make_plan(Prime(nm, p, "pseudo"))
+    assert isinstance(plan, PseudoMersenneBits)
+    L = plan.L
+    assert plan.bound == (1 << p.bit_length()) + (1 << 32) and plan.R == 1
+    b = plan.blocks
+    assert b["mul"].stats()[0] == L * L + L and b["sqr"].stats()[0] == L * (L + 1) // 2 + L
+    assert b["add"].stats()[0] == 0 and b["sub"].stats()[0] == 0
+    for seed in (3, 4):
+        assert plan.self_check(trials=300, seed=seed)
+    # the fall-back plan still takes the same modulus (comparison builds: MAB_PMBITS=0)
+    assert MontgomeryFull(Prime(nm, p, "monty")).build()

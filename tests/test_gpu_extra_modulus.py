@@ -16,6 +16,9 @@ from oracle_primes import OraclePrime
 pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 P384 = 2**384 - 2**128 - 2**96 + 2**32 - 1            # monty.py named table, "NIST384"
+# add-on moduli: NIST384 takes the fall-back plan (full Montgomery); 2^414 - 17 (13 limbs, two spare bits) and
+# 2^521 - 1 (17 limbs, 23 spare bits) take the bit-level pseudo-Mersenne plan (pseudo.py named table)
+ADDONS = {"NIST384": P384, "C41417": 2**414 - 17, "NIST521": 2**521 - 1}
 
 
 @pytest.fixture(scope="module")
@@ -30,16 +33,28 @@ def _bytes(t):
     return t.cpu().numpy()
 
 
-def test_field_ops_vs_reference_build(F):
+@pytest.mark.parametrize("name", list(ADDONS))
+def test_field_ops_vs_reference_build(name):
     import ctypes
-    path = os.path.join(ROOT, "oracle", "_ref", "libref_NIST384.so")
+    from modarith_b200 import Field, lib as mlib
+    if not os.path.exists(mlib.extra_lib_path(name)):
+        pytest.fail("libmodarith_b200_%s.so is missing: __graft_entry__.build() builds it" % name)
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_%s.so" % name)
     if not os.path.exists(path):
         pytest.skip("oracle/_ref not built")
     ref = ctypes.CDLL(path)
+    F = Field(name)
+    p = ADDONS[name]
     nb, n = F.Nbytes, 1 << 12
-    assert nb == 48 and F.Nlimbs == 12
+    assert nb == (p.bit_length() + 7) // 8 and F.Nlimbs == (p.bit_length() + 31) // 32
     a, b = util.random_bytes(384, n, nb), util.random_bytes(385, n, nb)
-    for i, v in enumerate([P384 - 1, P384, P384 + 1, (1 << 384) - 1, 0, 1]):
+    top = 1 << p.bit_length()
+    # the reference's modimp takes values below 2p: keep the random rows inside the field's bit length
+    spare = 8 * nb - p.bit_length()
+    if spare:
+        a[:, 0] &= 0xFF >> spare
+        b[:, 0] &= 0xFF >> spare
+    for i, v in enumerate([p - 1, p, p + 1, top - 1, 0, 1, p - 2, (p + top) // 2]):
         a[i] = np.frombuffer(v.to_bytes(nb, "big"), dtype=np.uint8)
     x, st = F.modimp(torch.from_numpy(a).cuda())
     y, _ = F.modimp(torch.from_numpy(b).cuda())
@@ -52,8 +67,57 @@ def test_field_ops_vs_reference_build(F):
         if op == "sqrt": F.modsqrt(x, None, r)
         if op == "add": F.modadd(x, y, r)
         if op == "sub": F.modsub(x, y, r)
-        assert np.array_equal(_bytes(F.modexp(r)), want), op
-        assert np.array_equal(st.cpu().numpy(), wst)
+        assert np.array_equal(_bytes(F.modexp(r)), want), (name, op)
+        assert np.array_equal(st.cpu().numpy(), wst), (name, op)
+
+
+@pytest.mark.parametrize("name", ["C41417", "NIST521"])
+def test_bit_level_pseudo_mersenne_plan_api_vs_oracle(name):
+    """The rest of the API on the bit-level plan (values stored below 2^n + 2^32, raw imports up to 2^(32L))."""
+    from modarith_b200 import Field
+    p = ADDONS[name]
+    F = Field(name)
+    O = FieldOracle(OraclePrime(name, p))
+    rng = random.Random(521)
+    xs = [0, 1, 2, p - 1, p - 2, (p - 1) // 2] + [rng.randrange(p) for _ in range(300)]
+    ys = [p - 1, 0, 1, 2, p - 1, 3] + [rng.randrange(p) for _ in range(300)]
+    x, y = F.from_ints(xs), F.from_ints(ys)
+    r = F.alloc(len(xs))
+    F.modneg(x, r); assert F.to_ints(r) == [O.modneg(a) for a in xs]
+    F.modmli(x, 121665, r); assert F.to_ints(r) == [O.modmli(a, 121665) for a in xs]
+    F.modmli(x, (1 << 31) - 1, r); assert F.to_ints(r) == [O.modmli(a, (1 << 31) - 1) for a in xs]
+    F.modcpy(x, r); F.modhaf(r); assert F.to_ints(r) == [O.modhaf(a) for a in xs]
+    F.modcpy(x, r); F.modnsqr(r, 5); assert F.to_ints(r) == [O.modnsqr(a, 5) for a in xs]
+    F.modpro(x, r); assert F.to_ints(r) == [O.modpro(a) for a in xs]
+    assert F.modqr(None, x).cpu().tolist() == [O.modqr(None, a) for a in xs]
+    assert F.modis0(x).cpu().tolist() == [int(a == 0) for a in xs]
+    assert F.modis1(x).cpu().tolist() == [int(a == 1) for a in xs]
+    assert F.modcmp(x, y).cpu().tolist() == [int(a == b) for a, b in zip(xs, ys)]
+    assert F.modsign(x).cpu().tolist() == [a & 1 for a in xs]
+    # a long chain keeps the representation inside its bound: ((x*y + x - y)^2 * 7 - x)^-1 ...
+    code = [("mul", 2, 0, 1), ("add", 2, 2, 0), ("sub", 2, 2, 1), ("sqr", 2, 2, 0), ("mli", 2, 2, 0, 7), ("sub", 2, 2, 0),
+            ("neg", 3, 2, 0), ("add", 3, 3, 3), ("mul", 3, 3, 2), ("inv", 4, 3, 0)]
+    def ref(a, b):
+        t = ((a * b + a - b) ** 2 * 7 - a) % p
+        u = (-t * 2 * t) % p
+        return pow(u, -1, p) if u else 0
+    want = [ref(a, b) for a, b in zip(xs, ys)]
+    for jit in (False, True):
+        (res,) = F.modprog(code, [x, y], [4], jit=jit)
+        assert F.to_ints(res) == want, (name, jit)
+    # raw words up to 2^(32L) through nres (modimp of words): canonical value and the "< p" flag
+    L = F.Nlimbs
+    topw = 1 << (32 * L)
+    raw = [topw - 1, topw - 2, p, p + 1, 2 * p, 3 * p + 5, topw >> 1, 0, p - 1] + [rng.randrange(topw) for _ in range(100)]
+    planes = np.zeros((L, len(raw)), dtype=np.uint32)
+    for i, v in enumerate(raw):
+        for j in range(L):
+            planes[j, i] = (v >> (32 * j)) & 0xFFFFFFFF
+    t = torch.from_numpy(planes.view(np.int32)).cuda()
+    flags = F.modfsb(t).cpu().tolist()
+    assert flags == [int(v < p) for v in raw]
+    got = t.cpu().numpy().view(np.uint32).astype(object)
+    assert [sum(int(got[j, i]) << (32 * j) for j in range(L)) for i in range(len(raw))] == [v % p for v in raw]
 
 
 def test_api_vs_oracle_and_programs(F):
