@@ -59,4 +59,31 @@ if "ecn" in what:
         for _ in range(2):
             ecnmul2(curve, e[:h], x[:h], y[:h], f[:h], x[:h], y[:h])
     torch.cuda.synchronize()
+if "jit" in what:
+    # compiled field programs (mab_<P>_modprog_jit): the P-256 point addition, the interpreter's kernel beside it
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_jit import POINT_ADD
+    F = Field("NIST256")
+    n = 1 << 21
+    ops = [F.modimp(torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g))[0] for _ in range(7)]
+    outs = [F.alloc(n) for _ in range(3)]
+    for jit in (True, False):
+        for _ in range(2):
+            F.modprog(POINT_ADD, ops, [12, 13, 14], outputs=outs, jit=jit)     # k_prog_jit / k_prog<F_NIST256>
+    torch.cuda.synchronize()
+if "addon" in what:
+    # add-on moduli on the bit-level pseudo-Mersenne plan and the user-curve ladder
+    for name in ("C41417", "NIST521"):
+        F = Field(name)
+        n = 1 << 20
+        x, _ = F.modimp(torch.randint(0, 128, (n, F.Nbytes), dtype=torch.uint8, device=dev, generator=g))
+        y, _ = F.modimp(torch.randint(0, 128, (n, F.Nbytes), dtype=torch.uint8, device=dev, generator=g))
+        r = F.alloc(n)
+        for _ in range(2):
+            F.bench_modmul(x, y, r, 128)
+    k = torch.randint(0, 256, (1 << 19, 48), dtype=torch.uint8, device=dev, generator=g)
+    u = torch.randint(0, 256, (1 << 19, 48), dtype=torch.uint8, device=dev, generator=g)
+    for _ in range(2):
+        rfc7748("M383", k, u)
+    torch.cuda.synchronize()
 print("done")

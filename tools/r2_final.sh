@@ -15,11 +15,13 @@ timeout 900 ncu --set full --clock-control none -k regex:'k_rfc7748_rounds' -s 1
 timeout 900 ncu --set full --clock-control none -k regex:'k_field' -c 8 -o gpurun_out/r2f_p256 python tools/ncu_targets.py p256 > gpurun_out/ncu_c.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:'k_field' -c 8 -o gpurun_out/r2f_k1 python tools/ncu_targets.py k1 > gpurun_out/ncu_d.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:'k_ecnmul' -c 8 -o gpurun_out/r2f_ecn python tools/ncu_targets.py ecn > gpurun_out/ncu_e.log 2>&1
-for f in x25519 x448 p256 k1 ecn; do
+timeout 900 ncu --set full --clock-control none -k regex:'k_prog' -s 2 -c 4 -o gpurun_out/r2f_jit python tools/ncu_targets.py jit > gpurun_out/ncu_f.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:'k_field|k_rfc7748_rounds' -c 6 -o gpurun_out/r2f_addon python tools/ncu_targets.py addon > gpurun_out/ncu_g.log 2>&1
+for f in x25519 x448 p256 k1 ecn jit addon; do
   ncu -i gpurun_out/r2f_$f.ncu-rep --page raw --csv > gpurun_out/r2f_$f.csv 2>/dev/null
   python tools/ncu_summary.py gpurun_out/r2f_$f.csv > gpurun_out/r2_ncu_$f.txt
 done
-rm -f gpurun_out/r2f_x448.ncu-rep gpurun_out/r2f_p256.ncu-rep gpurun_out/r2f_k1.ncu-rep gpurun_out/r2f_ecn.ncu-rep
+rm -f gpurun_out/r2f_x448.ncu-rep gpurun_out/r2f_p256.ncu-rep gpurun_out/r2f_k1.ncu-rep gpurun_out/r2f_ecn.ncu-rep gpurun_out/r2f_jit.ncu-rep gpurun_out/r2f_addon.ncu-rep
 head -30 gpurun_out/r2_ncu_x25519.txt
 # sanitizers on the small smoke
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/r2_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/r2_sanitizer_memcheck.log
