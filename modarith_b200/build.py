@@ -141,6 +141,9 @@ def build_extra(name, expr=None, force=False, verbose=True, curve=None):
         a24, cof, gen = (int(v) for v in curve)
         if not (0 < a24 < 2**31 and cof in (2, 3) and 0 < gen < 2**31):
             raise ValueError("curve constants: 0 < a24 < 2^31, cof 2 or 3 (rfc7748.c:121-131), 0 < generator < 2^31")
+        if P.nbytes % 4 != 0:
+            raise ValueError("the ladder kernels move whole 32-bit words: a curve needs a modulus of 32k-24 .. 32k bits "
+                             "(Nbytes = %d here)" % P.nbytes)
         P = Prime(P.name, P.p, P.family, a24=a24, cof=cof, generator=gen)
     build(verbose=False)                                   # the runtime objects and the common JIT sources
     ext = os.path.join(OBJDIR, "ext")

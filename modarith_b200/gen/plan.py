@@ -1314,6 +1314,28 @@ class MontgomeryFull(Montgomery):
         return asm
 
 
+class MontgomeryFriendly(MontgomeryFull):
+    """Montgomery form, R = 2^(32L), for a modulus with p = -1 (mod 2^(32z)), z >= 1 whole words: p + 1 = 2^(32z) * q.
+    The quotient digits are the low words themselves and only the L - z words of q are multiplied
+    (satmul.montgomery_friendly): L^2 + L(L - z) wide multiplies per modmul instead of the fall-back plan's 2 L^2 + L.
+    What monty.py's named table holds beyond the NIST shapes is mostly of this kind: 2^a 3^b - 1 (z = 6 .. 11 of
+    14 .. 24 words), 3*67*2^246 - 1 and 5*2^248 - 1 (z = 7 of 8), 2^n - 2^m - 1 (z = m div 32), P-384 (z = 1)
+    (monty.py:1961-2108)."""
+
+    def __init__(self, prime):
+        MontgomeryFull.__init__(self, prime)
+        z = 0
+        while (prime.p + 1) % (1 << (32 * (z + 1))) == 0:
+            z += 1
+        assert 1 <= z < self.L, "p + 1 has no whole zero word at the bottom"
+        self.z = z
+        self.q = (prime.p + 1) >> (32 * z)
+
+    def _mont(self, asm, a, b):
+        L = self.L
+        return self._cond_sub_p9(asm, satmul.montgomery_friendly(asm, a, b, words(self.q, L - self.z), self.z))
+
+
 def make_plan(prime: Prime) -> Plan:
     """Choose the cheapest plan whose preconditions hold for this modulus (cf. the radix /
     strategy decisions of pseudo.py:1569-1678 and monty.py:2140-2248); MontgomeryFull accepts
@@ -1330,7 +1352,10 @@ def make_plan(prime: Prime) -> Plan:
         cands.append(PseudoMersenne33)
     if 0 < c < (1 << 15) and 32 * L - n >= 2 and os.environ.get("MAB_PMBITS", "1") != "0":
         cands.append(PseudoMersenneBits)
-    cands += [Montgomery, MontgomeryFull]
+    cands += [Montgomery]
+    if (p + 1) % (1 << 32) == 0 and os.environ.get("MAB_MFRIENDLY", "1") != "0":
+        cands.append(MontgomeryFriendly)
+    cands.append(MontgomeryFull)
     err = None
     for cls in cands:
         try:

@@ -101,6 +101,21 @@ def _row_chain(asm: Asm, acc: _Acc, prods, nwords, carry_in=False):
             asm.add(nhi, hi, 0, cin=True, cout=False)
             acc.reg[top], acc.reg[top + 1] = nlo, nhi
             acc.ub[top], acc.ub[top + 1] = vmax & M32 if (vmax >> 32) == 0 else M32, min(M32, vmax >> 32)
+        elif acc.live[top] and acc.ub[top] == M32:
+            # the word above the row is a full word of another row (rows shorter than the ones before them:
+            # montgomery_friendly): the carry ripples on until a word that can absorb it
+            asm.wide_chain(slots, last_carry_to=None, carry_in=carry_in, keep_carry=True)
+            w = top
+            while True:
+                more = acc.live[w] and acc.ub[w] == M32 and w + 1 < nwords
+                d = asm.tmp()
+                asm.add(d, acc.src(w), 0, cin=True, cout=more)
+                was = acc.ub[w] if acc.live[w] else 0
+                acc.reg[w], acc.live[w] = d, True
+                acc.ub[w] = min(M32, was + 1)
+                if not more:
+                    break
+                w += 1
         else:
             c = acc.src(top)
             asm.wide_chain(slots, last_carry_to=(acc.dst(top), c), carry_in=carry_in)
@@ -321,6 +336,86 @@ def montgomery_interleaved(asm: Asm, a, b, pw, n0):
         _row_chain(asm, Y, [(i + j, pw[j], m) for j in range(1, L, 2)], n, carry_in=carry)
         _row_chain(asm, X, [(i + j, pw[j], m) for j in range(0, L, 2)], n)
     # words below L are zero (or dead); the result is E + O over words L .. 2L
+    T = []
+    started = False
+    for k in range(L, 2 * L + 1):
+        e, o = E.src(k), O.src(k)
+        if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
+            T.append(o if (isinstance(e, int) and e == 0) else e)
+            continue
+        d = asm.tmp()
+        asm.add(d, e, o, cin=started, cout=(k < 2 * L))
+        started = True
+        T.append(d)
+    return T
+
+
+def montgomery_friendly(asm: Asm, a, b, q, z):
+    """a*b*2^(-32L) mod p before the final conditional subtraction (L+1 words, < 2p) for a modulus with
+    p = -1 (mod 2^(32z)), z >= 1: p + 1 = 2^(32z) * q.  Then -p^-1 = 1 (mod 2^(32z)), so the quotient digit of a
+    z-word block is the block itself, and T + m*p = T - m + m*q*2^(32z): the low z words cancel WITHOUT a single
+    instruction and only the L - z words of q are multiplied (monty.py:740-751 calls the one-word case "Montgomery
+    friendly"; isogeny and MFP primes have z up to L - 1).  L^2 + L(L - z) wide multiplies and no plain ones, where
+    `montgomery_interleaved` needs 2 L^2 + L.
+
+    Rounds are taken z at a time on the even/odd accumulators of `product_eo`: the product rows a*b[i] of a block,
+    then ONE add-with-carry chain E[k] + O[k] over the block's z words -- the sums are the digits m_k, and the chain's
+    carry has exactly the weight of word i0 + z, where the first row m*q starts: it is that chain's carry-in -- then
+    the rows m_k*q at word k + z.  Words below L are never touched again and never read."""
+    L = len(a)
+    nq = len(q)
+    assert len(b) == L and 1 <= z < L and nq == L - z
+    n = 2 * L + 2
+    E, O = _Acc(asm, n), _Acc(asm, n)
+
+    def arrays(s):
+        return (E, O) if s % 2 == 0 else (O, E)
+
+    for i0 in range(0, L, z):
+        blk = list(range(i0, min(L, i0 + z)))
+        for i in blk:
+            if isinstance(b[i], int) and b[i] == 0:
+                continue
+            X, Y = arrays(i)
+            _row_chain(asm, X, [(i + j, a[j], b[i]) for j in range(0, L, 2)], n)
+            _row_chain(asm, Y, [(i + j, a[j], b[i]) for j in range(1, L, 2)], n)
+        # the digits of the block: m_k = (E[k] + O[k] + carry) mod 2^32
+        m = {}
+        started = False
+        for k in blk:
+            e, o = E.src(k), O.src(k)
+            if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
+                m[k] = o if (isinstance(e, int) and e == 0) else e       # nothing to add: no carry can arise
+                continue
+            d = asm.tmp()
+            asm.add(d, e, o, cin=started, cout=True)
+            started = True
+            m[k] = d
+        # a short block (the last one when z does not divide L): the chain goes on over the words up to i0 + z - 1,
+        # which merges them into E, so that its carry still has the weight of the word where the rows start
+        for k in range(blk[-1] + 1, i0 + z):
+            e, o = E.src(k), O.src(k)
+            if not started and (isinstance(e, int) or isinstance(o, int)) and (e == 0 or o == 0):
+                if isinstance(e, int) and e == 0 and not isinstance(o, int):
+                    E.reg[k], E.live[k], E.ub[k] = O.reg[k], True, O.ub[k]
+                    O.reg[k], O.live[k], O.ub[k] = asm.tmp(), False, 0
+                continue
+            d = asm.tmp()
+            asm.add(d, e, o, cin=started, cout=True)
+            started = True
+            E.reg[k], E.live[k], E.ub[k] = d, True, M32
+            O.reg[k], O.live[k], O.ub[k] = asm.tmp(), False, 0
+        carry = started
+        for k in blk:
+            if isinstance(m[k], int) and m[k] == 0:                       # leading zero rows of b: digit 0, no carry yet
+                assert not carry
+                continue
+            X, Y = arrays(k + z)
+            ev = [(k + z + t, q[t], m[k]) for t in range(0, nq, 2)]         # windows of the parity of k + z
+            od = [(k + z + t, q[t], m[k]) for t in range(1, nq, 2)]
+            _row_chain(asm, X, ev, n, carry_in=carry)                     # the block's first row takes the digit chain's carry
+            carry = False
+            _row_chain(asm, Y, od, n)
     T = []
     started = False
     for k in range(L, 2 * L + 1):

@@ -60,6 +60,8 @@ TARGETS = [
     # two spare bits, 2^521 - 1 on 17 limbs with 23 (pseudo.py named table)
     ("C41417", "pseudo.py", "C41417", True, False),
     ("NIST521", "pseudo.py", "NIST521", True, False),
+    # p = -1 (mod 2^(32z)): the generator's Montgomery-friendly plan (5*2^248 - 1: z = 7 of 8 words)
+    ("ED248", "monty.py", "ED248", True, False),
 ]
 # a user-defined Montgomery curve (y^2 = x^3 + 2065150 x^2 + x over 2^383 - 187, a24 = (A - 2) / 4, cofactor 8, base
 # point u = 12): backs the test of an add-on library WITH a ladder (python -m modarith_b200.build --prime M383=... --a24 ...)

@@ -6,7 +6,7 @@ import pytest
 
 from modarith_b200.primes import ALL_PRIMES as PRIMES, Prime
 from modarith_b200.gen.plan import (make_plan, PseudoMersenne, PseudoMersenne33, PseudoMersenneBits, GenMersenne, Montgomery,
-                                    MontgomeryFull, words, value)
+                                    MontgomeryFriendly, MontgomeryFull, words, value)
 from modarith_b200.gen.ptx import Asm, LostCarry
 from modarith_b200.gen import satmul
 from modarith_b200.gen.emit import emit_field_header
@@ -124,3 +124,21 @@ def test_bit_level_pseudo_mersenne_plan(nm, expr):
         assert plan.self_check(trials=300, seed=seed)
     # the fall-back plan still takes the same modulus (comparison builds: MAB_PMBITS=0)
     assert MontgomeryFull(Prime(nm, p, "monty")).build()
+
+
+@pytest.mark.parametrize("nm,expr,z", [("ED248", "5*2**248-1", 7), ("MFP4", "3*67*(2**246)-1", 7), ("SIDH434", "2**216*3**137-1", 6),
+                                       ("GM270", "2**270-2**162-1", 5), ("GM512", "2**512-2**127-1", 3),
+                                       ("NIST384", "2**384-2**128-2**96+2**32-1", 1)])
+def test_montgomery_friendly_plan(nm, expr, z):
+    """p = -1 (mod 2^(32z)): the quotient digits are the low words themselves and only the L - z high words of
+    (p + 1) / 2^(32z) are multiplied -- L^2 + L(L - z) wide multiplies, no plain ones (monty.py:740-751 is the
+    one-word case; isogeny, MFP and 2^n - 2^m - 1 primes of monty.py:1961-2108 have z up to L - 1)."""
+    p = eval(expr)
+    plan = make_plan(Prime(nm, p, "monty"))
+    assert isinstance(plan, MontgomeryFriendly) and plan.z == z
+    L = plan.L
+    assert plan.blocks["mul"].stats()[:2] == (L * L + L * (L - z), 0)
+    assert plan.self_check(trials=120, seed=5)
+    full = MontgomeryFull(Prime(nm, p, "monty"))
+    full.build()
+    assert full.blocks["mul"].stats()[0] == 2 * L * L

@@ -16,9 +16,11 @@ from oracle_primes import OraclePrime
 pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 P384 = 2**384 - 2**128 - 2**96 + 2**32 - 1            # monty.py named table, "NIST384"
-# add-on moduli: NIST384 takes the fall-back plan (full Montgomery); 2^414 - 17 (13 limbs, two spare bits) and
+# add-on moduli: 2^414 - 17 (13 limbs, two spare bits) and
 # 2^521 - 1 (17 limbs, 23 spare bits) take the bit-level pseudo-Mersenne plan (pseudo.py named table)
-ADDONS = {"NIST384": P384, "C41417": 2**414 - 17, "NIST521": 2**521 - 1}
+# 5*2^248 - 1 (monty.py named table "ED248") and NIST384 itself are p = -1 (mod 2^(32z)), z = 7 and 1: the
+# Montgomery-friendly plan
+ADDONS = {"NIST384": P384, "C41417": 2**414 - 17, "NIST521": 2**521 - 1, "ED248": 5 * 2**248 - 1}
 
 
 @pytest.fixture(scope="module")
