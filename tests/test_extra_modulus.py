@@ -47,8 +47,8 @@ def test_names_and_missing_libraries_fail_with_instructions():
         build.build_extra("no-such name")
     with pytest.raises(KeyError):
         build.build_extra("NOSUCHPRIME")
-    with pytest.raises(mlib.MabError, match="--prime C41417"):
-        mlib.load_for("C41417")
+    with pytest.raises(mlib.MabError, match="--prime GM240"):
+        mlib.load_for("GM240")
 
 
 def test_every_named_modulus_of_the_reference_has_a_plan():
