@@ -55,6 +55,19 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------
+def workload_config(n_local, world):
+    """The `config` object of the JSON line; both arms print exactly this for the same --gpus / --keys, so that the
+    driver's comparison of the two lines sees one workload (what differs between the arms -- the CPU sample of each
+    reference step -- is said in `cpu_baseline.sample`)."""
+    nsets = 3 if n_local * 3 * 32 <= (1 << 30) else 1
+    return {"workload": "batched X25519 (rfc7748) 2^20 random scalars/points per GPU" if n_local == 1 << 20
+            else "batched X25519 (rfc7748) %d random scalars/points per GPU" % n_local,
+            "keys_per_gpu": n_local, "keys_total": n_local * world, "sharding": "contiguous key ranges, no collective",
+            "l2": ("inputs rotate over 3 buffer sets (288 MB > 126 MB L2); kernel moves 96 B/key" if nsets == 3 else
+                   "one buffer set of %d MB (>> 126 MB L2); kernel moves 96 B/key" % (n_local * 3 * 32 >> 20)),
+            "inputs": "numpy PCG64(7748+...) raw bytes, unclamped / unreduced"}
+
+
 def make_inputs(n, seed):
     import numpy as np
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -427,8 +440,7 @@ def run_reference(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (radix 2^51) on CPU",
         "data": "synthetic",
-        "config": {"workload": "batched X25519 (rfc7748) 2^20 random scalars/points per GPU", "keys_per_gpu": args.keys,
-                   "cpu_sample_keys_per_step": n, "inputs": "numpy PCG64(7748) raw bytes, unclamped / unreduced"},
+        "config": workload_config(args.keys, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": "scalar-mults/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "scalar-mults/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -725,12 +737,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (saturated radix 2^32)",
             "data": "synthetic",
-            "config": {"workload": "batched X25519 (rfc7748) 2^20 random scalars/points per GPU" if n_local == 1 << 20
-                       else "batched X25519 (rfc7748) %d random scalars/points per GPU" % n_local,
-                       "keys_per_gpu": n_local, "keys_total": n_total, "sharding": "contiguous key ranges, no collective",
-                       "l2": ("inputs rotate over 3 buffer sets (288 MB > 126 MB L2); kernel moves 96 B/key" if NSETS == 3 else
-                              "one buffer set of %d MB (>> 126 MB L2); kernel moves 96 B/key" % (n_local * 3 * NB >> 20)),
-                       "inputs": "numpy PCG64(7748+...) raw bytes, unclamped / unreduced"},
+            "config": workload_config(n_local, world),
             "e2e": {"value": e2e, "unit": "scalar-mults/s", "h2d_bytes_per_step": 2 * NB * n_local,
                     "d2h_bytes_per_step": NB * n_local, "ms_per_step": e2e_ms / args.steps,
                     "ms_per_step_min_median_max_rank0": [1e3 * min(e2e_steps), 1e3 * statistics.median(e2e_steps),
