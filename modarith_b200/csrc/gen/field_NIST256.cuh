@@ -2246,12 +2246,12 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t22, %9, %12, t22;\n\t"
         "madc.lo.cc.u32 t23, %9, %14, t23;\n\t"
         "madc.hi.cc.u32 t24, %9, %14, t24;\n\t"
-        "addc.u32 t25, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t25, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t6, %10, %12, t6;\n\t"
         "madc.hi.cc.u32 t7, %10, %12, t7;\n\t"
         "madc.lo.cc.u32 t8, %10, %14, t8;\n\t"
         "madc.hi.cc.u32 t9, %10, %14, t9;\n\t"
-        "addc.u32 t10, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t10, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t21, %10, %11, t21;\n\t"
         "madc.hi.cc.u32 t22, %10, %11, t22;\n\t"
         "madc.lo.cc.u32 t23, %10, %13, t23;\n\t"
@@ -2266,10 +2266,10 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t24, %11, %12, t24;\n\t"
         "madc.lo.cc.u32 t25, %11, %14, t25;\n\t"
         "madc.hi.cc.u32 t26, %11, %14, t26;\n\t"
-        "addc.u32 t27, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t27, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t10, %12, %14, t10;\n\t"
         "madc.hi.cc.u32 t11, %12, %14, t11;\n\t"
-        "addc.u32 t12, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t12, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t25, %12, %13, t25;\n\t"
         "madc.hi.cc.u32 t26, %12, %13, t26;\n\t"
         "madc.lo.cc.u32 t27, %12, %15, t27;\n\t"
@@ -2278,7 +2278,7 @@ struct F_NIST256 {
         "madc.hi.u32 t13, %13, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t27, %13, %14, t27;\n\t"
         "madc.hi.cc.u32 t28, %13, %14, t28;\n\t"
-        "addc.u32 t29, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t29, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t29, %14, %15, t29;\n\t"
         "madc.hi.cc.u32 t30, %14, %15, 0x0;\n\t"
         "addc.cc.u32 t32, t2, t18;\n\t"
@@ -2294,7 +2294,7 @@ struct F_NIST256 {
         "addc.cc.u32 t42, t12, t28;\n\t"
         "addc.cc.u32 t43, t13, t29;\n\t"
         "addc.cc.u32 t44, 0x0, t30;\n\t"
-        "addc.u32 t45, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t45, 0, 0, 0;\n\t"
         "shl.b32 t46, t17, 1;\n\t"
         "shf.l.wrap.b32 t47, t17, t32, 1;\n\t"
         "shf.l.wrap.b32 t48, t32, t33, 1;\n\t"
@@ -2345,7 +2345,7 @@ struct F_NIST256 {
         "addc.cc.u32 t93, 0x0, t84;\n\t"
         "addc.cc.u32 t94, 0x0, t86;\n\t"
         "addc.cc.u32 t95, 0x0, 0x0;\n\t"
-        "addc.u32 t96, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t96, 0, 0, 0;\n\t"
         "add.cc.u32 t97, t89, t61;\n\t"
         "addc.cc.u32 t98, t90, t62;\n\t"
         "addc.cc.u32 t99, t91, t63;\n\t"
@@ -2376,7 +2376,7 @@ struct F_NIST256 {
         "addc.cc.u32 t124, t74, t111;\n\t"
         "addc.cc.u32 t125, t75, t112;\n\t"
         "addc.cc.u32 t126, t76, t113;\n\t"
-        "addc.u32 t127, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t127, 0, 0, 0;\n\t"
         "sub.u32 t128, 0x0, t127;\n\t"
         "and.b32 t129, t128, 0xfffffffe;\n\t"
         "add.cc.u32 t130, t119, t127;\n\t"

@@ -1136,6 +1136,10 @@ class Montgomery(Plan):
 
     def build_sqr_w(self):
         asm = Asm(self.name + ".sqr_w")
+        # 36 wide multiplies under ~90 add/sub-with-carry instructions: ALU-bound, so the nine carry captures go to
+        # the multiplier pipe (IMAD.X instead of SEL): modnsqr chain 138.6 -> 146.0 Gop/s, modinv per element
+        # 512 -> 530 Mop/s (profiles/r2_p256_capop.txt).  The same choice costs the multiplier-bound mul_w 2 %.
+        asm.capture_op = os.environ.get("MAB_CAPOP_SQRW", "madc")
         (a,) = self._io(asm, ["a"])
         T = satmul.square(asm, a, link=self.link_products)
         self._outs(asm, self._redc(asm, T, weak=True))

@@ -20,7 +20,14 @@ shr shfl shfr mov prmt, with optional carry-in / carry-out flags.
 """
 from __future__ import annotations
 
+import os
+
 M32 = 0xFFFFFFFF
+# How a carry capture (addc d, 0, 0) is emitted: "addc" leaves the choice to ptxas (SEL on the ALU pipe), "madc" writes
+# madc.lo d, 0, 0, 0, which ptxas turns into IMAD.X on the multiplier pipe.  Multiplier-bound functions want the first,
+# ALU-bound ones the second (profiles/r2_p256_capop.txt); a plan sets Asm.capture_op per function, MAB_CAPOP overrides
+# the default of every function for experiments.
+CAPTURE_OP = os.environ.get("MAB_CAPOP", "addc")
 
 
 class LostCarry(Exception):
@@ -36,6 +43,7 @@ class Asm:
         self.outputs = []      # (external output name, internal reg)
         self.nocheck = set()   # instruction indices allowed to wrap (borrow-mask captures)
         self.zero_cin = set()  # instruction indices whose carry-in is an ordering link: must be 0
+        self.capture_op = CAPTURE_OP
 
     # ---- registers ------------------------------------------------------
     def tmp(self, n=None):
@@ -279,6 +287,11 @@ class Asm:
             if op in ("add", "sub"):
                 m = ("addc" if cin else "add") if op == "add" else ("subc" if cin else "sub")
                 m += ".cc.u32" if cout else ".u32"
+                if self.capture_op == "madc" and op == "add" and cin and not cout and s[0] == 0 and s[1] == 0:
+                    # carry capture on the multiplier pipe (IMAD.X) instead of the ALU pipe (SEL): pays where a
+                    # function is ALU-bound
+                    lines.append("madc.lo.u32 %s, 0, 0, 0;" % o(d))
+                    continue
                 lines.append("%s %s, %s, %s;" % (m, o(d), o(s[0]), o(s[1])))
             elif op in ("madlo", "madhi"):
                 m = ("madc" if cin else "mad") + (".lo" if op == "madlo" else ".hi")
