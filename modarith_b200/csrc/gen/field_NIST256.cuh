@@ -67,7 +67,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t22, %12, %17, t22;\n\t"
         "madc.lo.cc.u32 t23, %14, %17, t23;\n\t"
         "madc.hi.cc.u32 t24, %14, %17, t24;\n\t"
-        "addc.u32 t25, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t25, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t2, %8, %18, t2;\n\t"
         "madc.hi.cc.u32 t3, %8, %18, t3;\n\t"
         "madc.lo.cc.u32 t4, %10, %18, t4;\n\t"
@@ -76,7 +76,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t7, %12, %18, t7;\n\t"
         "madc.lo.cc.u32 t8, %14, %18, t8;\n\t"
         "madc.hi.cc.u32 t9, %14, %18, t9;\n\t"
-        "addc.u32 t10, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t10, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t19, %9, %18, t19;\n\t"
         "madc.hi.cc.u32 t20, %9, %18, t20;\n\t"
         "madc.lo.cc.u32 t21, %11, %18, t21;\n\t"
@@ -101,7 +101,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t24, %12, %19, t24;\n\t"
         "madc.lo.cc.u32 t25, %14, %19, t25;\n\t"
         "madc.hi.cc.u32 t26, %14, %19, t26;\n\t"
-        "addc.u32 t27, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t27, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t4, %8, %20, t4;\n\t"
         "madc.hi.cc.u32 t5, %8, %20, t5;\n\t"
         "madc.lo.cc.u32 t6, %10, %20, t6;\n\t"
@@ -110,7 +110,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t9, %12, %20, t9;\n\t"
         "madc.lo.cc.u32 t10, %14, %20, t10;\n\t"
         "madc.hi.cc.u32 t11, %14, %20, t11;\n\t"
-        "addc.u32 t12, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t12, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t21, %9, %20, t21;\n\t"
         "madc.hi.cc.u32 t22, %9, %20, t22;\n\t"
         "madc.lo.cc.u32 t23, %11, %20, t23;\n\t"
@@ -135,7 +135,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t26, %12, %21, t26;\n\t"
         "madc.lo.cc.u32 t27, %14, %21, t27;\n\t"
         "madc.hi.cc.u32 t28, %14, %21, t28;\n\t"
-        "addc.u32 t29, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t29, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t6, %8, %22, t6;\n\t"
         "madc.hi.cc.u32 t7, %8, %22, t7;\n\t"
         "madc.lo.cc.u32 t8, %10, %22, t8;\n\t"
@@ -144,7 +144,7 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t11, %12, %22, t11;\n\t"
         "madc.lo.cc.u32 t12, %14, %22, t12;\n\t"
         "madc.hi.cc.u32 t13, %14, %22, t13;\n\t"
-        "addc.u32 t14, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t14, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t23, %9, %22, t23;\n\t"
         "madc.hi.cc.u32 t24, %9, %22, t24;\n\t"
         "madc.lo.cc.u32 t25, %11, %22, t25;\n\t"
@@ -204,7 +204,7 @@ struct F_NIST256 {
         "addc.cc.u32 t63, 0x0, t54;\n\t"
         "addc.cc.u32 t64, 0x0, t56;\n\t"
         "addc.cc.u32 t65, 0x0, 0x0;\n\t"
-        "addc.u32 t66, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t66, 0, 0, 0;\n\t"
         "add.cc.u32 t67, t59, t0;\n\t"
         "addc.cc.u32 t68, t60, t32;\n\t"
         "addc.cc.u32 t69, t61, t33;\n\t"
@@ -235,7 +235,7 @@ struct F_NIST256 {
         "addc.cc.u32 t94, t44, t81;\n\t"
         "addc.cc.u32 t95, t45, t82;\n\t"
         "addc.cc.u32 t96, t46, t83;\n\t"
-        "addc.u32 t97, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t97, 0, 0, 0;\n\t"
         "sub.cc.u32 t98, t89, 0xffffffff;\n\t"
         "subc.cc.u32 t99, t90, 0xffffffff;\n\t"
         "subc.cc.u32 t100, t91, 0xffffffff;\n\t"
@@ -577,12 +577,12 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t22, %9, %12, t22;\n\t"
         "madc.lo.cc.u32 t23, %9, %14, t23;\n\t"
         "madc.hi.cc.u32 t24, %9, %14, t24;\n\t"
-        "addc.u32 t25, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t25, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t6, %10, %12, t6;\n\t"
         "madc.hi.cc.u32 t7, %10, %12, t7;\n\t"
         "madc.lo.cc.u32 t8, %10, %14, t8;\n\t"
         "madc.hi.cc.u32 t9, %10, %14, t9;\n\t"
-        "addc.u32 t10, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t10, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t21, %10, %11, t21;\n\t"
         "madc.hi.cc.u32 t22, %10, %11, t22;\n\t"
         "madc.lo.cc.u32 t23, %10, %13, t23;\n\t"
@@ -597,10 +597,10 @@ struct F_NIST256 {
         "madc.hi.cc.u32 t24, %11, %12, t24;\n\t"
         "madc.lo.cc.u32 t25, %11, %14, t25;\n\t"
         "madc.hi.cc.u32 t26, %11, %14, t26;\n\t"
-        "addc.u32 t27, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t27, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t10, %12, %14, t10;\n\t"
         "madc.hi.cc.u32 t11, %12, %14, t11;\n\t"
-        "addc.u32 t12, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t12, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t25, %12, %13, t25;\n\t"
         "madc.hi.cc.u32 t26, %12, %13, t26;\n\t"
         "madc.lo.cc.u32 t27, %12, %15, t27;\n\t"
@@ -609,7 +609,7 @@ struct F_NIST256 {
         "madc.hi.u32 t13, %13, %15, 0x0;\n\t"
         "mad.lo.cc.u32 t27, %13, %14, t27;\n\t"
         "madc.hi.cc.u32 t28, %13, %14, t28;\n\t"
-        "addc.u32 t29, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t29, 0, 0, 0;\n\t"
         "mad.lo.cc.u32 t29, %14, %15, t29;\n\t"
         "madc.hi.cc.u32 t30, %14, %15, 0x0;\n\t"
         "addc.cc.u32 t32, t2, t18;\n\t"
@@ -625,7 +625,7 @@ struct F_NIST256 {
         "addc.cc.u32 t42, t12, t28;\n\t"
         "addc.cc.u32 t43, t13, t29;\n\t"
         "addc.cc.u32 t44, 0x0, t30;\n\t"
-        "addc.u32 t45, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t45, 0, 0, 0;\n\t"
         "shl.b32 t46, t17, 1;\n\t"
         "shf.l.wrap.b32 t47, t17, t32, 1;\n\t"
         "shf.l.wrap.b32 t48, t32, t33, 1;\n\t"
@@ -676,7 +676,7 @@ struct F_NIST256 {
         "addc.cc.u32 t93, 0x0, t84;\n\t"
         "addc.cc.u32 t94, 0x0, t86;\n\t"
         "addc.cc.u32 t95, 0x0, 0x0;\n\t"
-        "addc.u32 t96, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t96, 0, 0, 0;\n\t"
         "add.cc.u32 t97, t89, t61;\n\t"
         "addc.cc.u32 t98, t90, t62;\n\t"
         "addc.cc.u32 t99, t91, t63;\n\t"
@@ -707,7 +707,7 @@ struct F_NIST256 {
         "addc.cc.u32 t124, t74, t111;\n\t"
         "addc.cc.u32 t125, t75, t112;\n\t"
         "addc.cc.u32 t126, t76, t113;\n\t"
-        "addc.u32 t127, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t127, 0, 0, 0;\n\t"
         "sub.cc.u32 t128, t119, 0xffffffff;\n\t"
         "subc.cc.u32 t129, t120, 0xffffffff;\n\t"
         "subc.cc.u32 t130, t121, 0xffffffff;\n\t"
@@ -1539,7 +1539,7 @@ struct F_NIST256 {
         "addc.cc.u32 t5, %13, %21;\n\t"
         "addc.cc.u32 t6, %14, %22;\n\t"
         "addc.cc.u32 t7, %15, %23;\n\t"
-        "addc.u32 t8, 0x0, 0x0;\n\t"
+        "madc.lo.u32 t8, 0, 0, 0;\n\t"
         "sub.cc.u32 t9, t0, 0xffffffff;\n\t"
         "subc.cc.u32 t10, t1, 0xffffffff;\n\t"
         "subc.cc.u32 t11, t2, 0xffffffff;\n\t"

@@ -53,6 +53,7 @@ class Plan:
     link_products = False
     family = "?"
     tight = None            # exclusive bound of mul/sqr outputs when it is below 2^(32L) (see PseudoMersenne)
+    capture_ops = {}        # function -> "madc" where its carry captures belong on the multiplier pipe (see build)
 
     def __init__(self, prime: Prime):
         self.P = prime
@@ -90,6 +91,12 @@ class Plan:
         if getattr(self, "weak_bound", None):
             self.blocks["mul_w"] = self.build_mul_w()
             self.blocks["sqr_w"] = self.build_sqr_w()
+        # which pipe a function's carry captures run on (ptx.py: "addc" = ptxas' choice, SEL on the ALU pipe; "madc" =
+        # IMAD.X on the multiplier pipe): the plan's table, then MAB_CAPOP_<PRIME>_<FUNCTION>=madc|addc for experiments
+        for fn, asm in self.blocks.items():
+            v = os.environ.get("MAB_CAPOP_%s_%s" % (self.name.upper(), fn.upper()), self.capture_ops.get(fn))
+            if v:
+                asm.capture_op = v
         return self.blocks
 
     def _io(self, asm, ins, out="r"):
@@ -987,6 +994,11 @@ class Montgomery(Plan):
     spare bit for the reference's lazy "< 2p" results."""
     family = "monty"
     link_products = os.environ.get("MAB_LINK", "1") != "0"
+    # Everything on this plan except the multiplication chain is ALU-bound (the reduction is add/sub-with-carry chains),
+    # so the carry captures go to the multiplier pipe: modnsqr chain 138.6 -> 146.0 Gop/s, modinv per element 512 -> 530
+    # Mop/s, ecnmul 21.66 -> 22.08 M/s (profiles/r2_p256_capop.txt, r2_ecn_capop.txt).  mul_w, which sits on the
+    # boundary of the two regimes, loses 2 % with the same choice and keeps ptxas' SEL.
+    capture_ops = {"mul": "madc", "sqr": "madc", "add": "madc", "sub": "madc", "sqr_w": "madc"}
 
     def __init__(self, prime):
         super().__init__(prime)
@@ -1136,10 +1148,6 @@ class Montgomery(Plan):
 
     def build_sqr_w(self):
         asm = Asm(self.name + ".sqr_w")
-        # 36 wide multiplies under ~90 add/sub-with-carry instructions: ALU-bound, so the nine carry captures go to
-        # the multiplier pipe (IMAD.X instead of SEL): modnsqr chain 138.6 -> 146.0 Gop/s, modinv per element
-        # 512 -> 530 Mop/s (profiles/r2_p256_capop.txt).  The same choice costs the multiplier-bound mul_w 2 %.
-        asm.capture_op = os.environ.get("MAB_CAPOP_SQRW", "madc")
         (a,) = self._io(asm, ["a"])
         T = satmul.square(asm, a, link=self.link_products)
         self._outs(asm, self._redc(asm, T, weak=True))
@@ -1233,6 +1241,8 @@ class MontgomeryFull(Montgomery):
         a*b*R^-1 = (T + U) / R               one 2L-word add chain, one conditional subtraction
 
     Stored values are fully reduced, in [0, p)."""
+
+    capture_ops = {}        # multiplier-bound: ptxas' choice
 
     def __init__(self, prime):
         Plan.__init__(self, prime)
