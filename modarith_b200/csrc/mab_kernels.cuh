@@ -405,7 +405,9 @@ template <class F, bool VALIDATE = false> __global__ void MAB_LADDER_BOUNDS(F) k
 // scheduler favoured (the sub-partition arbiter is not fair) take more of them and all finish together.
 // A warp whose queue is empty steals from the other queues, which also makes the result independent of
 // where the CTAs were placed.  Small batches (grid below full residency) use one queue.
-#define MAB_LADDER_KMAX 4
+#ifndef MAB_LADDER_KMAX
+#define MAB_LADDER_KMAX 4             // 4 or 2 (-DMAB_LADDER_KMAX=2: occupancy experiments; the host cuts no K = 4 chunks then)
+#endif
 struct MabQueues {
   unsigned long long* counter;     // nq counters, zeroed before the launch
   unsigned nq;                     // number of queues
