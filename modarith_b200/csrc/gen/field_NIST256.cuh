@@ -22,7 +22,7 @@ struct F_NIST256 {
   static constexpr int PM1D2 = 1;
   static constexpr bool MONTGOMERY = true;
   static constexpr int PRO_SQR = 253, PRO_MUL = 12;
-  static constexpr int LADDER_MINBLOCKS = 4;   // resident 128-thread CTAs per SM for k_rfc7748
+  static constexpr int LADDER_MINBLOCKS = 3;   // resident 128-thread CTAs per SM for k_rfc7748
   static constexpr bool LADDER_STASH = false;   // scalar and x1 in shared memory (see rfc7748_sm100.cuh)
   static constexpr bool HAS_CURVE = false;
   static constexpr uint32_t A24 = 0;

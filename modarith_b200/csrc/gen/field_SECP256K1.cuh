@@ -20,7 +20,7 @@ struct F_SECP256K1 {
   static constexpr int PM1D2 = 1;
   static constexpr bool MONTGOMERY = false;
   static constexpr int PRO_SQR = 253, PRO_MUL = 18;
-  static constexpr int LADDER_MINBLOCKS = 4;   // resident 128-thread CTAs per SM for k_rfc7748
+  static constexpr int LADDER_MINBLOCKS = 3;   // resident 128-thread CTAs per SM for k_rfc7748
   static constexpr bool LADDER_STASH = false;   // scalar and x1 in shared memory (see rfc7748_sm100.cuh)
   static constexpr bool HAS_CURVE = false;
   static constexpr uint32_t A24 = 0;

@@ -367,7 +367,7 @@ template <class F> __global__ void __launch_bounds__(128) k_exp(const uint32_t* 
 #define MAB_LADDER_THREADS 128
 #endif
 // resident CTAs per SM the ladder is compiled for: chosen per modulus by the generator
-// (F::LADDER_MINBLOCKS: 4 for X25519 = 110 registers, no spills) unless overridden for experiments
+// (F::LADDER_MINBLOCKS: 3 for X25519 = 146 registers in k_rfc7748_rounds, no spills) unless overridden for experiments
 #ifdef MAB_LADDER_MINBLOCKS
 #define MAB_LADDER_BOUNDS(F) __launch_bounds__(MAB_LADDER_THREADS, MAB_LADDER_MINBLOCKS)
 #else

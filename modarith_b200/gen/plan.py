@@ -62,8 +62,10 @@ class Plan:
         self.L = (prime.nbits + 31) // 32
         self.bound = 1 << (32 * self.L)      # exclusive bound on stored values (overridden)
         self.R = 1                           # Montgomery factor (1 = plain residues)
-        # launch bound of the ladder kernel (measured on B200: X25519 runs best at 4 CTAs/SM, 126-128 registers, no spill)
-        self.ladder_minblocks = int(os.environ.get("MAB_MINBLOCKS_" + prime.name, 4 if self.L <= 8 else 2))
+        # launch bound of the ladder kernel.  8 limbs: three resident CTAs per SM -- ptxas then takes the 146 registers it
+        # wants for the round-structured kernel, and the same step loop (identical opcode mix) runs 1-7 % faster than the
+        # 128-register allocation four CTAs force, at every batch size (profiles/r2_x25519_occupancy.txt); more limbs: two
+        self.ladder_minblocks = int(os.environ.get("MAB_MINBLOCKS_" + prime.name, 3 if self.L <= 8 else 2))
         self.ladder_stash = os.environ.get("MAB_STASH_" + prime.name, "1" if self.L > 8 else "0") == "1"
 
     # -- representation -----------------------------------------------------

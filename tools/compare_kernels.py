@@ -11,7 +11,7 @@ from modarith_b200 import lib as mlib  # noqa: E402
 l = mlib.load()
 st = torch.cuda.current_stream().cuda_stream
 for curve, nb in (("X25519", 32), ("X448", 56)):
-    for lg in (20, 22):
+    for lg in [int(v) for v in os.environ.get("LGS", "20 22").split()]:
         n = 1 << lg
         g = torch.Generator(device="cuda").manual_seed(1)
         k = torch.randint(0, 256, (n, nb), dtype=torch.uint8, device="cuda", generator=g)
