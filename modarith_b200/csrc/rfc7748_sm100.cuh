@@ -10,6 +10,13 @@
 #pragma once
 #include "mab_field.cuh"
 
+// experiment switch: -DMAB_STEP_UNROLL2 unrolls the step loop twice (lets ptxas overlap the ALU-only head of a step with
+// the multiplications that end the step before it)
+#ifdef MAB_STEP_UNROLL2
+#define MAB_STEP_UNROLL _Pragma("unroll 2")
+#else
+#define MAB_STEP_UNROLL MAB_NOUNROLL
+#endif
 // experiment switch: -DMAB_NO_TAIL_DOUBLING runs all Nbits steps through the full ladder step
 #ifdef MAB_NO_TAIL_DOUBLING
 #define MAB_TAIL_DOUBLINGS(F) 0
@@ -81,7 +88,7 @@ template <class F> struct Rfc7748 {
       // the lowest COF bits of a clamped scalar are zero (rfc7748.c:137): those steps are plain
       // doublings of (x2:z2) and are done after the loop without the differential-addition half
       const int nb = (w == L - 1) ? topbits : (w == 0 ? 32 - MAB_TAIL_DOUBLINGS(F) : 32);
-      MAB_NOUNROLL
+      MAB_STEP_UNROLL
       for (int bi = 0; bi < nb; bi++) {
         uint32_t kt = kw >> 31;
         kw <<= 1;
