@@ -16,5 +16,5 @@ for f in ("gpurun_out/r2_bench_n${N}_torchrun.json", "gpurun_out/r2_bench_n${N}_
     except Exception as e:
         print(f, "unreadable", e)
 PY
-SWEEP_LGS="20 22 24 26 28" timeout 1500 bash tools/sweep.sh $N 2>&1 | tail -8
+SWEEP_LGS="${SWEEP_LGS:-20 22 24 26 28}" timeout 1500 bash tools/sweep.sh $N 2>&1 | tail -8
 cp gpurun_out/sweep_n$N.jsonl gpurun_out/r2_sweep_n$N.jsonl
