@@ -7,6 +7,7 @@
 // bytes[i*Nbytes ..], modimp/modexp big-endian, rfc7748 little-endian) and are moved with
 // the widest vector access the pointer alignment allows.
 #pragma once
+#include "mab_queue_plan.h"
 #include <cuda_runtime.h>
 #include "modarith_b200.h"
 #include "rfc7748_sm100.cuh"
@@ -424,15 +425,7 @@ static __device__ __forceinline__ void mab_queue_range(const MabQueues& Q, unsig
   lo = (unsigned long long)q * Q.base + (q < Q.rem ? q : Q.rem);
   g = Q.base + longer;
 }
-// chunk ci of a queue: returns K (0 = past the end) and the first group of the chunk inside the queue
-static __device__ __forceinline__ int mab_queue_chunk(unsigned g, unsigned c4, unsigned c2, unsigned long long ci, unsigned& first) {
-  if (ci < c4) { first = (unsigned)ci * 4; return 4; }
-  if (ci < (unsigned long long)c4 + c2) { first = c4 * 4 + (unsigned)(ci - c4) * 2; return 2; }
-  const unsigned long long s = (unsigned long long)c4 * 4 + (unsigned long long)c2 * 2 + (ci - c4 - c2);
-  if (s >= g) return 0;
-  first = (unsigned)s;
-  return 1;
-}
+// chunk ci of a queue -> K and the first group: mab_queue_chunk (mab_queue_plan.h, shared with the host and the CPU tests)
 template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const uint8_t* bk, const uint8_t* bu, uint8_t* bv, size_t n, unsigned align, MabQueues Q) {
   constexpr int L = F::L;
   constexpr int T = MAB_LADDER_THREADS;
@@ -472,7 +465,7 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
             unsigned long long lo2; unsigned g2, lg2;
             mab_queue_range(Q, qq, lo2, g2, lg2);
             const unsigned c4 = lg2 ? Q.c4l : Q.c4s, c2 = lg2 ? Q.c2l : Q.c2s;
-            has = *(volatile unsigned long long*)(Q.counter + qq) < (unsigned long long)(c4 + c2 + (g2 - 4 * c4 - 2 * c2));
+            has = *(volatile unsigned long long*)(Q.counter + qq) < (unsigned long long)mab_queue_nchunks(g2, c4, c2);
           }
           const unsigned m = __ballot_sync(0xffffffffu, has);
           if (m) {
@@ -489,7 +482,7 @@ template <class F> __global__ void MAB_LADDER_BOUNDS(F) k_rfc7748_rounds(const u
       unsigned g, longer;
       mab_queue_range(Q, q, glo, g, longer);
       const unsigned c4 = longer ? Q.c4l : Q.c4s, c2 = longer ? Q.c2l : Q.c2s;
-      const unsigned nchunks = c4 + c2 + (g - 4 * c4 - 2 * c2);
+      const unsigned nchunks = mab_queue_nchunks(g, c4, c2);
       unsigned long long ci = 0;
       int ok = 0;
       if (lane == 0) {
