@@ -142,3 +142,43 @@ def test_montgomery_friendly_plan(nm, expr, z):
     full = MontgomeryFull(Prime(nm, p, "monty"))
     full.build()
     assert full.blocks["mul"].stats()[0] == 2 * L * L
+
+
+def test_carry_capture_pipe_table(monkeypatch):
+    """Which pipe a function's carry captures run on is a per-plan table (Plan.capture_ops): the ALU-bound P-256 plan
+    writes them as madc.lo d, 0, 0, 0 (IMAD.X) everywhere but in mul_w, the multiplier-bound plans leave `addc d, 0, 0`
+    to ptxas; MAB_CAPOP_<PRIME>_<FN> overrides one function (profiles/r2_p256_capop.txt, r2_ecn_capop.txt)."""
+    def captures(asm):
+        lines, _, _ = asm.emit_ptx()
+        return (sum(1 for l in lines if l.startswith("madc.lo.u32") and l.endswith(", 0, 0, 0;")),
+                sum(1 for l in lines if l.startswith("addc.u32") and l.endswith(", 0x0, 0x0;")))
+
+    p256 = make_plan(PRIMES["NIST256"])
+    b = p256.build()
+    for fn in ("mul", "sqr", "add", "sub", "sqr_w"):
+        assert b[fn].capture_op == "madc"
+    assert b["mul_w"].capture_op == "addc"
+    m, a = captures(b["sqr_w"])
+    assert m >= 5 and a == 0
+    m, a = captures(b["mul_w"])
+    assert m == 0 and a >= 5
+    for name in ("X25519", "X448", "SECP256K1", "NIST256ORDER"):
+        for fn, asm in make_plan(PRIMES[name]).build().items():
+            assert asm.capture_op == "addc", (name, fn)
+            assert captures(asm)[0] == 0
+    monkeypatch.setenv("MAB_CAPOP_NIST256_SQR_W", "addc")
+    monkeypatch.setenv("MAB_CAPOP_X25519_SQR", "madc")
+    assert make_plan(PRIMES["NIST256"]).build()["sqr_w"].capture_op == "addc"
+    x = make_plan(PRIMES["X25519"]).build()
+    assert x["sqr"].capture_op == "madc" and x["mul"].capture_op == "addc"
+    # the interpreter sees the same instruction either way: results do not depend on the table
+    assert make_plan(PRIMES["NIST256"]).build() and p256.self_check(trials=50, seed=7)
+
+
+def test_ladder_launch_bounds():
+    """8-limb ladders are compiled for three resident CTAs per SM (ptxas then takes the registers it wants:
+    profiles/r2_x25519_occupancy.txt), longer ones for two; MAB_MINBLOCKS_<PRIME> overrides."""
+    assert make_plan(PRIMES["X25519"]).ladder_minblocks == 3
+    assert make_plan(PRIMES["X448"]).ladder_minblocks == 2
+    hdr = open(os.path.join(ROOT, "modarith_b200", "csrc", "gen", "field_X25519.cuh")).read()
+    assert "LADDER_MINBLOCKS = 3;" in hdr
