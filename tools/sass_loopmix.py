@@ -8,6 +8,10 @@ For each backward branch the instructions between its target and the branch are 
   I     other IMAD.* / IMAD.HI  (multiplier pipe, 2 cycles; .HI 4)
   A     everything else that executes on the ALU pipe (IADD3, LOP3, SHF, SEL, MOV, ...)
 and the issue model fitted in profiles/r2_issue_probe.txt is evaluated on them.
+
+The count is STATIC: a loop whose body holds both arms of a run-time choice shows both (the X448 ladder step carries
+the z3 = x1 * (DA-CB)^2 product twice, once per arm of `if (stash)`: 1600 wide multiplies in the listing, 1404 executed
+per step -- DESIGN.md section 9, item 4).
 """
 import collections
 import re
